@@ -1,0 +1,64 @@
+"""ctypes binding of libckfft_b200.so -- the C ABI declared in include/ckfft/ckfft.h and
+include/ckfft/ckfft_b200.h.  Fails loudly when the library is missing: there is no Python or CPU
+fallback for any transform."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "lib", "libckfft_b200.so")
+
+# every symbol the two public headers declare (tests check the .so exports exactly these)
+CLASSIC_SYMBOLS = ["CkFftInit", "CkFftRealForward", "CkFftRealInverse", "CkFftComplexForward",
+                   "CkFftComplexInverse", "CkFftShutdown"]
+B200_SYMBOLS = ["CkFftComplexForwardBatch", "CkFftComplexInverseBatch", "CkFftRealForwardBatch",
+                "CkFftRealInverseBatch", "CkFftComplexForwardBatchAsync", "CkFftComplexInverseBatchAsync",
+                "CkFftRealForwardBatchAsync", "CkFftRealInverseBatchAsync", "CkFftB200GetPlan",
+                "CkFftB200LastError", "CkFftB200KernelLaunches", "CkFftB200HostAlloc", "CkFftB200HostFree",
+                "CkFftB200ContextDevice"]
+
+
+class Plan(C.Structure):
+    """CkFftB200Plan (include/ckfft/ckfft_b200.h)."""
+    _fields_ = [("n", C.c_int), ("isReal", C.c_int), ("complexPoints", C.c_int), ("passes", C.c_int),
+                ("radix", (C.c_int * 3) * 2), ("threadsPerTransform", C.c_int), ("elemsPerThread", C.c_int),
+                ("transformsPerCta", C.c_int), ("sharedBytes", C.c_int)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m ckfft_b200.build` (needs nvcc). "
+            "ckfft_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, i = C.c_void_p, C.c_size_t, C.c_int
+    lib.CkFftInit.restype = vp
+    lib.CkFftInit.argtypes = [i, i, vp, C.POINTER(sz)]
+    lib.CkFftShutdown.restype = None
+    lib.CkFftShutdown.argtypes = [vp]
+    for name in ("CkFftComplexForward", "CkFftComplexInverse", "CkFftRealForward"):
+        getattr(lib, name).argtypes = [vp, i, vp, vp]
+    lib.CkFftRealInverse.argtypes = [vp, i, vp, vp, vp]
+    for name in ("CkFftComplexForwardBatch", "CkFftComplexInverseBatch", "CkFftRealForwardBatch"):
+        getattr(lib, name).argtypes = [vp, i, vp, vp, sz]
+    lib.CkFftRealInverseBatch.argtypes = [vp, i, vp, vp, vp, sz]
+    for name in ("CkFftComplexForwardBatchAsync", "CkFftComplexInverseBatchAsync", "CkFftRealForwardBatchAsync",
+                 "CkFftRealInverseBatchAsync"):
+        getattr(lib, name).argtypes = [vp, i, vp, vp, sz, sz, sz, vp]
+    lib.CkFftB200GetPlan.argtypes = [i, i, C.POINTER(Plan)]
+    lib.CkFftB200LastError.restype = C.c_char_p
+    lib.CkFftB200KernelLaunches.restype = C.c_ulonglong
+    lib.CkFftB200HostAlloc.restype = vp
+    lib.CkFftB200HostAlloc.argtypes = [sz]
+    lib.CkFftB200HostFree.restype = None
+    lib.CkFftB200HostFree.argtypes = [vp]
+    lib.CkFftB200ContextDevice.argtypes = [vp]
+    _lib = lib
+    return lib

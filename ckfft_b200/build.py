@@ -1,0 +1,92 @@
+#!/usr/bin/env python3
+"""In-tree build of libckfft_b200.so (nvcc, sm_100a only).
+
+    python -m ckfft_b200.build            # incremental
+    python -m ckfft_b200.build --force
+
+The library is a plain C-ABI shared object (include/ckfft/*.h); nothing in it depends on torch or
+Python.  Objects are compiled in parallel (the single-pass kernel family is instantiated once per
+variant, see csrc/fft_variants.cu) and linked with the static CUDA runtime, so the .so is
+self-contained and travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+OBJ = os.path.join(PKG, "build")
+LIB = os.path.join(PKG, "lib", "libckfft_b200.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-std=c++17", "-O3", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-fvisibility=default",
+          f"-I{os.path.join(ROOT, 'include')}", f"-I{CSRC}"]
+
+# (object name, source, extra flags)
+UNITS = [
+    ("api.o", "api.cu", []),
+    ("tiny.o", "tiny.cu", []),
+    ("c2c_fwd.o", "fft_variants.cu", ["-DCKB_VARIANT=0"]),
+    ("c2c_inv.o", "fft_variants.cu", ["-DCKB_VARIANT=1"]),
+    ("r2c.o", "fft_variants.cu", ["-DCKB_VARIANT=2"]),
+    ("c2r.o", "fft_variants.cu", ["-DCKB_VARIANT=3"]),
+]
+
+
+def _source_stamp() -> str:
+    h = hashlib.sha256()
+    for d in (CSRC, os.path.join(ROOT, "include", "ckfft")):
+        for name in sorted(os.listdir(d)):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode())
+                h.update(f.read())
+    h.update(" ".join(COMMON).encode())
+    return h.hexdigest()
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: " + " ".join(cmd) + "\n" + r.stdout)
+    return r.stdout
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    stamp_file = os.path.join(OBJ, "stamp")
+    stamp = _source_stamp()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return LIB
+    if not os.path.exists(NVCC):
+        if os.path.exists(LIB):
+            # GPU box without a toolkit: use the library that travelled with the snapshot
+            return LIB
+        raise RuntimeError(f"nvcc not found at {NVCC} and no prebuilt {LIB}")
+    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+
+    def compile_unit(unit):
+        obj, src, extra = unit
+        cmd = [NVCC, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", os.path.join(OBJ, obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        out = _run(cmd)
+        if verbose:
+            print(out)
+        return os.path.join(OBJ, obj)
+
+    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(compile_unit, UNITS))
+    _run([NVCC, *ARCH, "-shared", "-o", LIB, *objs])
+    with open(stamp_file, "w") as f:
+        f.write(stamp)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

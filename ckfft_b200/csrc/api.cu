@@ -1,0 +1,530 @@
+// api.cu -- the C ABI of libckfft_b200.so: ckfft's six classic entry points plus the batched /
+// stream-ordered variants declared in include/ckfft/ckfft_b200.h.
+//
+// Host-side mirror of the reference's API layer and context:
+//   argument validation      src/ckfft/ckfft.cpp:14-119   (same checks, same 1/0/NULL returns)
+//   context + twiddle tables src/ckfft/context.cpp:24-122 (same size-query / user-buffer protocol,
+//                                                          same fp32 table formula)
+//   size dispatch            src/ckfft/fft.cpp:13-46, src/ckfft/fft_real.cpp:13-105
+// The arithmetic itself is in the CUDA kernels (fft_kernel.cuh, tiny_kernel.cuh, four_step.cu).
+// There is no CPU path: without a usable GPU CkFftInit returns NULL and says why through
+// CkFftB200LastError().
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+
+#include "ckfft/ckfft.h"
+#include "ckfft/ckfft_b200.h"
+#include "launch.h"
+#include "plans.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+// The first five members mirror the reference's struct (src/ckfft/context.h:4-19) so that code
+// which reaches behind the ABI the way the reference's own harness does (src/test/test.cpp:245-261
+// writes context->neon) keeps working.  `neon` is always false here.
+struct _CkFftContext
+{
+    bool neon;
+    int maxCount;
+    const CkFftComplex* fwdExpTable;   // host copy, NULL unless the Forward bit was requested
+    const CkFftComplex* invExpTable;   // host copy, NULL unless the Inverse bit was requested
+    bool ownBuf;
+
+    // --- B200 part ---
+    uint32_t magic;
+    int device;
+    int tableCount;          // Nt = min(maxCount, CKB_MAX_TABLE): entries in the device table
+    int log2Table;
+    float2* dTable;          // device: W_Nt^k = (cos, sin)(-2 pi k / Nt), forward sign
+};
+
+namespace {
+
+constexpr uint32_t kMagic = 0x434b4232u;   // "CKB2"
+
+thread_local char tl_error[256] = "";
+
+void set_error(const char* what, cudaError_t e = cudaSuccess)
+{
+    if (e != cudaSuccess) snprintf(tl_error, sizeof(tl_error), "%s: %s", what, cudaGetErrorString(e));
+    else                  snprintf(tl_error, sizeof(tl_error), "%s", what);
+}
+
+std::atomic<unsigned long long> g_launches{0};
+
+inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+inline int ilog2i(long long x) { int l = 0; while ((1LL << l) < x) ++l; return l; }
+
+// RAII: make the context's device current for the duration of a call
+struct DeviceGuard
+{
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        else if (prev == dev) prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+size_t context_bytes() { return (sizeof(_CkFftContext) + 7) & ~size_t(7); }
+
+enum Kind { K_C2C_FWD, K_C2C_INV, K_R2C, K_C2R };
+
+inline size_t in_elems(Kind k, int n)  { return k == K_C2R ? (size_t) n / 2 + 1 : (size_t) n; }
+inline size_t out_elems(Kind k, int n) { return k == K_R2C ? (size_t) n / 2 + 1 : (size_t) n; }
+inline size_t in_elem_bytes(Kind k)  { return k == K_R2C ? 4 : 8; }
+inline size_t out_elem_bytes(Kind k) { return k == K_C2R ? 4 : 8; }
+
+// Enqueue `batch` transforms on DEVICE memory.  Strides are in elements of the respective array.
+// Returns cudaSuccess or the launch error.
+cudaError_t enqueue(const _CkFftContext* c, Kind kind, int n, const void* in, void* out, long long batch,
+                    long long in_stride, long long out_stride, cudaStream_t s)
+{
+    using namespace ckb;
+    if (batch <= 0) return cudaSuccess;
+    const cf* table = c->dTable;
+    if (kind == K_C2C_FWD || kind == K_C2C_INV) {
+        KernelParams p{ (const cf*) in, (cf*) out, table, c->log2Table, batch, in_stride, out_stride };
+        const bool inv = kind == K_C2C_INV;
+        if (n <= 8) return launch_tiny_c2c(n, inv, p, s);
+        if (n <= CKB_MAX_SINGLE_PASS) return inv ? launch_c2c_inv(n, p, s) : launch_c2c_fwd(n, p, s);
+        return cudaErrorNotSupported;
+    }
+    if (n <= 16) {
+        return kind == K_R2C
+            ? launch_tiny_r2c(n, (const float*) in, (cf*) out, table, c->log2Table, batch, in_stride, out_stride, s)
+            : launch_tiny_c2r(n, (const cf*) in, (float*) out, table, c->log2Table, batch, in_stride, out_stride, s);
+    }
+    const int M = n / 2;
+    if (M <= CKB_MAX_SINGLE_PASS && n <= c->tableCount) {
+        // the cooperative kernel addresses both arrays in 8-byte units
+        if (kind == K_R2C) {
+            KernelParams p{ (const cf*) in, (cf*) out, table, c->log2Table, batch, in_stride / 2, out_stride };
+            return launch_r2c(M, p, s);
+        }
+        KernelParams p{ (const cf*) in, (cf*) out, table, c->log2Table, batch, in_stride, out_stride / 2 };
+        return launch_c2r(M, p, s);
+    }
+    return cudaErrorNotSupported;
+}
+
+// the reference's checks for one transform call (src/ckfft/ckfft.cpp:36-114), plus count <= 0
+bool check_call(const _CkFftContext* c, Kind kind, int n, const void* in, const void* out)
+{
+    if (!c || c->magic != kMagic) { set_error("invalid context"); return false; }
+    const bool needs_inv = (kind == K_C2C_INV || kind == K_C2R);
+    if (needs_inv ? !c->invExpTable : !c->fwdExpTable) { set_error("context was not created for this direction"); return false; }
+    if (!is_pow2(n) || n > c->maxCount) { set_error("n must be a power of two <= nMax"); return false; }
+    if (!in || !out || in == out) { set_error("input/output must be distinct non-NULL buffers"); return false; }
+    return true;
+}
+
+// per-thread staging for host-pointer calls: no mutable state lives in the (shared) context
+struct Staging
+{
+    int device = -1;
+    static constexpr int kSlots = 3;
+    void* d_in[kSlots] = {nullptr, nullptr, nullptr};
+    void* d_out[kSlots] = {nullptr, nullptr, nullptr};
+    size_t in_cap = 0, out_cap = 0;
+    cudaStream_t stream[kSlots] = {nullptr, nullptr, nullptr};
+
+    void release()
+    {
+        if (device < 0) return;
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaSetDevice(device);
+        for (int i = 0; i < kSlots; ++i) {
+            if (d_in[i]) cudaFree(d_in[i]);
+            if (d_out[i]) cudaFree(d_out[i]);
+            if (stream[i]) cudaStreamDestroy(stream[i]);
+            d_in[i] = d_out[i] = nullptr;
+            stream[i] = nullptr;
+        }
+        in_cap = out_cap = 0;
+        if (prev >= 0) cudaSetDevice(prev);
+        device = -1;
+    }
+    cudaError_t reserve(int dev, size_t in_bytes, size_t out_bytes)
+    {
+        if (device != dev) { release(); device = dev; }
+        cudaError_t e;
+        for (int i = 0; i < kSlots; ++i)
+            if (!stream[i] && (e = cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if (in_bytes > in_cap) {
+            for (int i = 0; i < kSlots; ++i) {
+                if (d_in[i]) cudaFree(d_in[i]);
+                d_in[i] = nullptr;
+                if ((e = cudaMalloc(&d_in[i], in_bytes)) != cudaSuccess) { in_cap = 0; return e; }
+            }
+            in_cap = in_bytes;
+        }
+        if (out_bytes > out_cap) {
+            for (int i = 0; i < kSlots; ++i) {
+                if (d_out[i]) cudaFree(d_out[i]);
+                d_out[i] = nullptr;
+                if ((e = cudaMalloc(&d_out[i], out_bytes)) != cudaSuccess) { out_cap = 0; return e; }
+            }
+            out_cap = out_bytes;
+        }
+        return cudaSuccess;
+    }
+    ~Staging() { /* process teardown: the driver reclaims device memory; cudaFree here could run after CUDA shutdown */ }
+};
+thread_local Staging tl_staging;
+
+enum Side { SIDE_HOST, SIDE_DEVICE, SIDE_BAD };
+
+Side classify(const void* p, int dev)
+{
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return SIDE_HOST; }
+    if (a.type == cudaMemoryTypeDevice) return a.device == dev ? SIDE_DEVICE : SIDE_BAD;
+    if (a.type == cudaMemoryTypeManaged) return SIDE_DEVICE;
+    return SIDE_HOST;   // unregistered or pinned host memory
+}
+
+// Host arrays: stream the batch through the GPU in chunks, three in flight
+// (H2D of chunk i+1, kernel of chunk i and D2H of chunk i-1 overlap on separate streams).
+int run_host(const _CkFftContext* c, Kind kind, int n, const void* in, void* out, size_t batch)
+{
+    const size_t ib = in_elems(kind, n) * in_elem_bytes(kind);     // bytes per transform
+    const size_t ob = out_elems(kind, n) * out_elem_bytes(kind);
+    const size_t target = size_t(32) << 20;                        // ~32 MiB of input per chunk
+    size_t per_chunk = target / ib;
+    if (per_chunk < 1) per_chunk = 1;
+    if (per_chunk > batch) per_chunk = batch;
+    // device buffers are padded to 16 bytes so that every slot keeps 8-byte aligned transforms
+    Staging& st = tl_staging;
+    cudaError_t e = st.reserve(c->device, per_chunk * ib + 16, per_chunk * ob + 16);
+    if (e != cudaSuccess) { set_error("staging allocation", e); return 0; }
+
+    size_t done = 0;
+    int slot = 0;
+    while (done < batch) {
+        const size_t cnt = (batch - done < per_chunk) ? batch - done : per_chunk;
+        cudaStream_t s = st.stream[slot];
+        // the slot's previous chunk must have drained before its buffers are reused
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) { set_error("stream sync", e); return 0; }
+        if ((e = cudaMemcpyAsync(st.d_in[slot], (const char*) in + done * ib, cnt * ib, cudaMemcpyHostToDevice, s)) != cudaSuccess) {
+            set_error("H2D copy", e); return 0;
+        }
+        e = enqueue(c, kind, n, st.d_in[slot], st.d_out[slot], (long long) cnt,
+                    (long long) in_elems(kind, n), (long long) out_elems(kind, n), s);
+        if (e != cudaSuccess) { set_error("kernel launch", e); return 0; }
+        if ((e = cudaMemcpyAsync((char*) out + done * ob, st.d_out[slot], cnt * ob, cudaMemcpyDeviceToHost, s)) != cudaSuccess) {
+            set_error("D2H copy", e); return 0;
+        }
+        done += cnt;
+        slot = (slot + 1) % Staging::kSlots;
+    }
+    for (int i = 0; i < Staging::kSlots; ++i)
+        if ((e = cudaStreamSynchronize(st.stream[i])) != cudaSuccess) { set_error("transform failed", e); return 0; }
+    return 1;
+}
+
+bool supported_size(const _CkFftContext* c, Kind kind, int n)
+{
+    if (kind == K_C2C_FWD || kind == K_C2C_INV) return n <= CKB_MAX_SINGLE_PASS;
+    return n <= 16 || (n / 2 <= CKB_MAX_SINGLE_PASS && n <= c->tableCount);
+}
+
+// shared body of the synchronous entry points
+int run_sync(CkFftContext* c, Kind kind, int n, const void* in, void* out, size_t batch)
+{
+    if (!check_call(c, kind, n, in, out)) return 0;
+    if (batch == 0) return 1;
+    if (!supported_size(c, kind, n)) { set_error("transform length not supported by this build"); return 0; }
+    DeviceGuard guard(c->device);
+    if (!guard.ok) { set_error("cannot select the context's device"); return 0; }
+    const Side si = classify(in, c->device), so = classify(out, c->device);
+    if (si == SIDE_BAD || so == SIDE_BAD || si != so) {
+        set_error("input and output must both be host memory or both be memory of the context's device");
+        return 0;
+    }
+    if (si == SIDE_HOST) return run_host(c, kind, n, in, out, batch);
+    if (((uintptr_t) in | (uintptr_t) out) & 7) { set_error("device pointers must be 8-byte aligned"); return 0; }
+    cudaError_t e = enqueue(c, kind, n, in, out, (long long) batch, (long long) in_elems(kind, n),
+                            (long long) out_elems(kind, n), cudaStreamPerThread);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
+    if (e != cudaSuccess) { set_error("transform failed", e); return 0; }
+    return 1;
+}
+
+int run_async(CkFftContext* c, Kind kind, int n, const void* in, void* out, size_t batch, size_t in_stride,
+              size_t out_stride, void* stream)
+{
+    if (!check_call(c, kind, n, in, out)) return 0;
+    if (batch == 0) return 1;
+    if (!supported_size(c, kind, n)) { set_error("transform length not supported by this build"); return 0; }
+    if (in_stride == 0) in_stride = in_elems(kind, n);
+    if (out_stride == 0) out_stride = out_elems(kind, n);
+    if (in_stride < in_elems(kind, n) || out_stride < out_elems(kind, n)) { set_error("stride shorter than one transform"); return 0; }
+    if (((uintptr_t) in | (uintptr_t) out) & 7) { set_error("device pointers must be 8-byte aligned"); return 0; }
+    if ((kind == K_R2C && n > 16 && (in_stride & 1)) || (kind == K_C2R && n > 16 && (out_stride & 1))) {
+        set_error("real-array strides must be even");
+        return 0;
+    }
+    DeviceGuard guard(c->device);
+    if (!guard.ok) { set_error("cannot select the context's device"); return 0; }
+    cudaError_t e = enqueue(c, kind, n, in, out, (long long) batch, (long long) in_stride, (long long) out_stride,
+                            (cudaStream_t) stream);
+    if (e != cudaSuccess) { set_error("kernel launch", e); return 0; }
+    return 1;
+}
+
+}  // namespace
+
+namespace ckb {
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int sm_count_of_current_device()
+{
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 1;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+}  // namespace ckb
+
+// ---------------------------------------------------------------------------------------------
+// exported C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+CkFftContext* CkFftInit(int maxCount, CkFftDirection direction, void* userBuf, size_t* userBufSize)
+{
+    // src/ckfft/ckfft.cpp:16-31
+    if (maxCount <= 0 || !is_pow2(maxCount)) { set_error("nMax must be a positive power of two"); return NULL; }
+    if (direction != kCkFftDirection_Forward && direction != kCkFftDirection_Inverse && direction != kCkFftDirection_Both) {
+        set_error("invalid direction");
+        return NULL;
+    }
+    if (userBuf && !userBufSize) { set_error("buf given without bufSize"); return NULL; }
+
+    // src/ckfft/context.cpp:27-51.  The host tables keep the reference's meaning (non-NULL table ==
+    // direction available) but only the Nt = min(nMax, CKB_MAX_TABLE) entries the kernels can use
+    // are materialised; larger transforms derive their twiddles on the device.
+    const int nt = maxCount < CKB_MAX_TABLE ? maxCount : CKB_MAX_TABLE;
+    const size_t tableBytes = (size_t) nt * sizeof(CkFftComplex);
+    size_t need = context_bytes();
+    if (direction & kCkFftDirection_Forward) need += tableBytes;
+    if (direction & kCkFftDirection_Inverse) need += tableBytes;
+    if (userBufSize && (!userBuf || *userBufSize < need)) {
+        *userBufSize = need;
+        return NULL;
+    }
+
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { set_error("no usable CUDA device (this library has no CPU path)", e); return NULL; }
+
+    void* buf = userBuf ? userBuf : malloc(need);
+    if (!buf) { set_error("out of host memory"); return NULL; }
+    _CkFftContext* c = new (buf) _CkFftContext();
+    memset(c, 0, sizeof(*c));
+
+    CkFftComplex* tab = (CkFftComplex*) ((char*) buf + context_bytes());
+    CkFftComplex* fwd = NULL;
+    CkFftComplex* inv = NULL;
+    if (direction & kCkFftDirection_Forward) { fwd = tab; tab += nt; }
+    if (direction & kCkFftDirection_Inverse) { inv = tab; }
+
+    // src/ckfft/context.cpp:90-105: the angle is formed in fp32 exactly like the reference, so the
+    // values are bit-identical to the reference table entries for the same angle
+    // (for power-of-two sizes table_Nt[k] == table_nMax[k * nMax / Nt]).
+    CkFftComplex* master = fwd ? fwd : inv;
+    for (int i = 0; i < nt; ++i) {
+        float theta = -2.0f * (float) M_PI * i / nt;
+        float cs = cosf(theta);
+        float sn = sinf(theta);
+        if (fwd) { fwd[i].real = cs; fwd[i].imag = sn; }
+        if (inv) { inv[i].real = cs; inv[i].imag = -sn; }
+    }
+
+    float2* dTable = NULL;
+    e = cudaMalloc((void**) &dTable, tableBytes);
+    if (e == cudaSuccess) {
+        if (fwd) {
+            e = cudaMemcpy(dTable, fwd, tableBytes, cudaMemcpyHostToDevice);
+        } else {
+            // device table always holds the forward sign; conjugate the inverse host table on the way
+            CkFftComplex* tmp = (CkFftComplex*) malloc(tableBytes);
+            if (!tmp) e = cudaErrorMemoryAllocation;
+            else {
+                for (int i = 0; i < nt; ++i) { tmp[i].real = master[i].real; tmp[i].imag = -master[i].imag; }
+                e = cudaMemcpy(dTable, tmp, tableBytes, cudaMemcpyHostToDevice);
+                free(tmp);
+            }
+        }
+    }
+    if (e != cudaSuccess) {
+        set_error("device twiddle table", e);
+        if (dTable) cudaFree(dTable);
+        if (!userBuf) free(buf);
+        return NULL;
+    }
+
+    c->neon = false;
+    c->maxCount = maxCount;
+    c->fwdExpTable = fwd;
+    c->invExpTable = inv;
+    c->ownBuf = (userBuf == NULL);
+    c->magic = kMagic;
+    c->device = dev;
+    c->tableCount = nt;
+    c->log2Table = ilog2i(nt);
+    c->dTable = dTable;
+    return c;
+}
+
+void CkFftShutdown(CkFftContext* c)
+{
+    // src/ckfft/context.cpp:116-122; device memory is ours whoever owns the host buffer
+    if (!c || c->magic != kMagic) return;
+    {
+        DeviceGuard guard(c->device);
+        if (c->dTable) cudaFree(c->dTable);
+    }
+    c->dTable = NULL;
+    c->magic = 0;
+    if (c->ownBuf) free(c);
+}
+
+int CkFftComplexForward(CkFftContext* c, int n, const CkFftComplex* in, CkFftComplex* out)
+{
+    return run_sync(c, K_C2C_FWD, n, in, out, 1);
+}
+
+int CkFftComplexInverse(CkFftContext* c, int n, const CkFftComplex* in, CkFftComplex* out)
+{
+    return run_sync(c, K_C2C_INV, n, in, out, 1);
+}
+
+int CkFftRealForward(CkFftContext* c, int n, const float* in, CkFftComplex* out)
+{
+    return run_sync(c, K_R2C, n, in, out, 1);
+}
+
+int CkFftRealInverse(CkFftContext* c, int n, const CkFftComplex* in, float* out, CkFftComplex* tmpBuf)
+{
+    if (!tmpBuf) { set_error("tmpBuf must not be NULL"); return 0; }   // src/ckfft/ckfft.cpp:57-60
+    return run_sync(c, K_C2R, n, in, out, 1);
+}
+
+int CkFftComplexForwardBatch(CkFftContext* c, int n, const CkFftComplex* in, CkFftComplex* out, size_t batch)
+{
+    return run_sync(c, K_C2C_FWD, n, in, out, batch);
+}
+
+int CkFftComplexInverseBatch(CkFftContext* c, int n, const CkFftComplex* in, CkFftComplex* out, size_t batch)
+{
+    return run_sync(c, K_C2C_INV, n, in, out, batch);
+}
+
+int CkFftRealForwardBatch(CkFftContext* c, int n, const float* in, CkFftComplex* out, size_t batch)
+{
+    return run_sync(c, K_R2C, n, in, out, batch);
+}
+
+int CkFftRealInverseBatch(CkFftContext* c, int n, const CkFftComplex* in, float* out, CkFftComplex* tmpBuf, size_t batch)
+{
+    (void) tmpBuf;
+    return run_sync(c, K_C2R, n, in, out, batch);
+}
+
+int CkFftComplexForwardBatchAsync(CkFftContext* c, int n, const CkFftComplex* in, CkFftComplex* out, size_t batch,
+                                  size_t inStride, size_t outStride, void* stream)
+{
+    return run_async(c, K_C2C_FWD, n, in, out, batch, inStride, outStride, stream);
+}
+
+int CkFftComplexInverseBatchAsync(CkFftContext* c, int n, const CkFftComplex* in, CkFftComplex* out, size_t batch,
+                                  size_t inStride, size_t outStride, void* stream)
+{
+    return run_async(c, K_C2C_INV, n, in, out, batch, inStride, outStride, stream);
+}
+
+int CkFftRealForwardBatchAsync(CkFftContext* c, int n, const float* in, CkFftComplex* out, size_t batch,
+                               size_t inStride, size_t outStride, void* stream)
+{
+    return run_async(c, K_R2C, n, in, out, batch, inStride, outStride, stream);
+}
+
+int CkFftRealInverseBatchAsync(CkFftContext* c, int n, const CkFftComplex* in, float* out, size_t batch,
+                               size_t inStride, size_t outStride, void* stream)
+{
+    return run_async(c, K_C2R, n, in, out, batch, inStride, outStride, stream);
+}
+
+int CkFftB200GetPlan(int n, int isReal, CkFftB200Plan* plan)
+{
+    if (!plan || !is_pow2(n)) return 0;
+    memset(plan, 0, sizeof(*plan));
+    plan->n = n;
+    plan->isReal = isReal ? 1 : 0;
+    const int m = isReal ? (n >= 2 ? n / 2 : 1) : n;
+    plan->complexPoints = m;
+    const bool tiny = isReal ? n <= 16 : n <= 8;
+    if (tiny) {
+        plan->passes = 1;
+        plan->radix[0][0] = m;
+        plan->threadsPerTransform = 1;
+        plan->elemsPerThread = m;
+        plan->transformsPerCta = 128;
+        return 1;
+    }
+    const ckb::PlanRow* r = ckb::find_plan(m);
+    if (!r || (isReal && n > CKB_MAX_TABLE)) return 0;
+    plan->passes = 1;
+    plan->radix[0][0] = r->R0;
+    plan->radix[0][1] = r->R1;
+    plan->radix[0][2] = r->R2 > 1 ? r->R2 : 0;
+    plan->threadsPerTransform = r->M / r->E;
+    plan->elemsPerThread = r->E;
+    plan->transformsPerCta = r->G;
+    plan->sharedBytes = r->smem_bytes;
+    return 1;
+}
+
+const char* CkFftB200LastError(void) { return tl_error; }
+
+unsigned long long CkFftB200KernelLaunches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void* CkFftB200HostAlloc(size_t bytes)
+{
+    void* p = NULL;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { set_error("pinned allocation", e); return NULL; }
+    return p;
+}
+
+void CkFftB200HostFree(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int CkFftB200ContextDevice(const CkFftContext* c) { return (c && c->magic == kMagic) ? c->device : -1; }
+
+}  // extern "C"

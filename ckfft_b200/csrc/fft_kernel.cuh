@@ -1,0 +1,276 @@
+// fft_kernel.cuh -- single-pass batched FFT kernel family for sm_100a (M = 16 .. 16384 complex points).
+//
+// One launch does one HBM read and one HBM write per transform.  It replaces the reference's
+// complex driver + recursion (src/ckfft/fft.cpp:13-46, src/ckfft/fft_default.cpp:12-266) and, in
+// the real modes, the split / twist passes (src/ckfft/fft_real_default.cpp:13-114) which are fused
+// into the same launch through shared memory.
+//
+// Structure (Stockham autosort, 2 or 3 radix stages, no bit-reversal pass):
+//   * a "group" of T = M/E threads owns one transform; every thread keeps E complex values in
+//     registers; G groups share a CTA;  CTAs are persistent and walk the batch grid-stride;
+//   * stage s loads x[j + t*M/R], multiplies by the stage twiddle W_{Ns*R}^{t*(j mod Ns)} taken
+//     from a shared-memory LUT laid out [t][j mod Ns] (immediate-offset, conflict-free LDS.64),
+//     runs an R-point register DFT (fft_regs.cuh) and scatters to (j/Ns)*Ns*R + (j mod Ns) + u*Ns;
+//   * the first stage reads global memory directly (every warp request is a run of contiguous
+//     8-byte elements: T*8 bytes per group, 256 B per warp when T >= 32), the last stage writes it
+//     the same way; stages in between exchange through a padded shared-memory buffer
+//     (index p -> p + p/R0: conflict-free for the stride-R0 scatter and for the unit-stride gather);
+//   * groups of <= 32 threads synchronise with __syncwarp only, larger groups with a named barrier.
+//
+// Twiddle values come from the context's device table W_Nt^k, which the host fills with the
+// reference's exact fp32 formula (src/ckfft/context.cpp:90-105), so every twiddle used here is
+// bit-identical to the table entry the reference would have used for the same angle.
+#pragma once
+#include "fft_regs.cuh"
+
+namespace ckb {
+
+enum Mode { MODE_C2C = 0, MODE_R2C = 1, MODE_C2R = 2 };
+
+struct KernelParams {
+    const cf* in;        // MODE_C2C/C2R: complex input; MODE_R2C: real input viewed as M complex
+    cf* out;             // MODE_C2C/R2C: complex output; MODE_C2R: real output viewed as M complex
+    const cf* table;     // W_Nt^k, k in [0, Nt)  (forward sign)
+    int log2_nt;         // log2(Nt)
+    long long batch;
+    long long in_stride;   // distance between consecutive transforms, in 8-byte units
+    long long out_stride;
+};
+
+template <int LOGPAD> __device__ __forceinline__ int padidx(int p) { return p + (p >> LOGPAD); }
+
+__device__ __forceinline__ cf ld_stream(const cf* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(cf* p, cf v) { __stcs(p, v); }
+
+__device__ __forceinline__ cf table_w(const cf* table, int idx, bool inverse)
+{
+    cf w = __ldg(table + idx);
+    if (inverse) w.y = -w.y;
+    return w;
+}
+
+template <int T>
+__device__ __forceinline__ void group_sync(int g)
+{
+    if constexpr (T <= 32) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(T) : "memory");
+    }
+}
+
+enum Src { SRC_GLOBAL = 0, SRC_XBUF = 1 };
+enum Dst { DST_GLOBAL = 0, DST_XCHG = 1, DST_XNAT = 2 };
+enum Tw { TW_NONE = 0, TW_LUT = 1, TW_TABLE = 2 };
+
+// One Stockham stage = gather + math + scatter over the E register values of a thread.  They are
+// separate so the kernel can put a group barrier between a shared-memory gather and the scatter
+// that reuses the same buffer.
+template <int M, int T, int E, int R, int LOGPAD, int SRC>
+__device__ __forceinline__ void stage_gather(cf (&v)[E], const cf* __restrict__ gsrc, const cf* xb, int j, bool valid)
+{
+    constexpr int B = E / R;      // butterflies per thread
+    constexpr int STR = M / R;    // distance between the R inputs of one butterfly
+    static_assert(B * R == E, "radix must divide the per-thread element count");
+    static_for<0, B>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        const int jq = j + q * T;
+        static_for<0, R>([&](auto t_) {
+            constexpr int t = decltype(t_)::value;
+            constexpr int slot = q * R + bitrev<R>(t);
+            if constexpr (SRC == SRC_GLOBAL) {
+                v[slot] = valid ? ld_stream(gsrc + jq + t * STR) : make_float2(0.f, 0.f);
+            } else {
+                v[slot] = xb[padidx<LOGPAD>(jq + t * STR)];
+            }
+        });
+    });
+}
+
+template <int T, int E, int R, int NS, bool INV, int TW>
+__device__ __forceinline__ void stage_math(cf (&v)[E], const cf* lut, const cf* __restrict__ table, int tshift, int j)
+{
+    constexpr int B = E / R;
+    if constexpr (TW != TW_NONE) {
+        static_for<0, B>([&](auto q_) {
+            constexpr int q = decltype(q_)::value;
+            const int m = (j + q * T) & (NS - 1);
+            static_for<1, R>([&](auto t_) {
+                constexpr int t = decltype(t_)::value;
+                constexpr int slot = q * R + bitrev<R>(t);
+                cf w;
+                if constexpr (TW == TW_LUT) w = lut[(t - 1) * NS + m];
+                else                        w = table_w(table, (t * m) << tshift, INV);
+                v[slot] = cmul(v[slot], w);
+            });
+        });
+    }
+    static_for<0, B>([&](auto q_) { fft_regs<R, decltype(q_)::value * R, INV>(v); });
+}
+
+template <int M, int T, int E, int R, int NS, int LOGPAD, int DST>
+__device__ __forceinline__ void stage_scatter(const cf (&v)[E], cf* __restrict__ gdst, cf* xb, int j, bool valid)
+{
+    constexpr int B = E / R;
+    constexpr int STR = M / R;
+    static_assert(DST != DST_GLOBAL || NS * R == M, "only the last stage writes global memory");
+    static_for<0, B>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        const int jq = j + q * T;
+        static_for<0, R>([&](auto u_) {
+            constexpr int u = decltype(u_)::value;
+            constexpr int slot = q * R + u;
+            if constexpr (DST == DST_GLOBAL) {
+                if (valid) st_stream(gdst + jq + u * STR, v[slot]);
+            } else if constexpr (DST == DST_XNAT) {
+                xb[padidx<LOGPAD>(jq + u * STR)] = v[slot];
+            } else {
+                const int p = (jq / NS) * (NS * R) + (jq & (NS - 1)) + u * NS;
+                xb[padidx<LOGPAD>(p)] = v[slot];
+            }
+        });
+    });
+}
+
+// Compile-time description of one kernel variant.
+template <int M_, int E_, int R0_, int R1_, int R2_, int G_, bool INV_, int MODE_, int MINB_ = 1>
+struct Cfg {
+    static constexpr int M = M_, E = E_, R0 = R0_, R1 = R1_, R2 = R2_, G = G_, MODE = MODE_, MINB = MINB_;
+    static constexpr bool INV = INV_;
+    static constexpr int T = M / E;
+    static constexpr int THREADS = G * T;
+    static constexpr int NSTAGE = R2 > 1 ? 3 : 2;
+    static constexpr int LOGPAD = ilog2(R0);
+    static constexpr int XBUF = M + (M >> LOGPAD) + 2;          // complex slots per group (+ slot M for the real modes)
+    static constexpr int LUT1 = (R1 - 1) * R0;                  // stage 1: Ns = R0
+    static constexpr bool LUT2_SMEM = NSTAGE == 3 && (R2 - 1) * R0 * R1 <= 4096;
+    static constexpr int LUT2 = LUT2_SMEM ? (R2 - 1) * R0 * R1 : 0;   // stage 2: Ns = R0*R1
+    static constexpr int SMEM_BYTES = 8 * (LUT1 + LUT2 + G * XBUF);
+    static_assert(R0 * R1 * R2 == M, "radices must multiply to the transform length");
+    static_assert(R0 <= E && R1 <= E && R2 <= E, "a butterfly must fit one thread");
+    static_assert(T <= 32 || G <= 15, "named barriers 1..15");
+    static_assert(THREADS <= 1024, "CTA too large");
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelParams p)
+{
+    constexpr int M = C::M, E = C::E, T = C::T, G = C::G, R0 = C::R0, R1 = C::R1, R2 = C::R2;
+    constexpr int LOGPAD = C::LOGPAD, MODE = C::MODE;
+    constexpr bool INV = C::INV;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf* lut1 = reinterpret_cast<cf*>(smem_raw);
+    cf* lut2 = lut1 + C::LUT1;
+    const int tid = threadIdx.x;
+    const int g = tid / T;
+    const int j = tid % T;
+    cf* xb = lut2 + C::LUT2 + g * C::XBUF;
+
+    // stage twiddle LUTs, [t-1][m] so that a thread's R-1 loads are immediate offsets from one base
+    {
+        const int sh1 = p.log2_nt - ilog2(R0 * R1);
+        for (int i = tid; i < C::LUT1; i += C::THREADS)
+            lut1[i] = table_w(p.table, ((i / R0 + 1) * (i % R0)) << sh1, INV);
+        if constexpr (C::LUT2 > 0) {
+            constexpr int NS2 = R0 * R1;
+            const int sh2 = p.log2_nt - ilog2(M);
+            for (int i = tid; i < C::LUT2; i += C::THREADS)
+                lut2[i] = table_w(p.table, ((i / NS2 + 1) * (i % NS2)) << sh2, INV);
+        }
+    }
+    __syncthreads();
+
+    const int sh_last = p.log2_nt - ilog2(M);        // W_M^k   = table[k << sh_last]
+    const int sh_real = p.log2_nt - ilog2(2 * M);    // W_2M^k  = table[k << sh_real]  (real modes)
+
+    for (long long base = (long long) blockIdx.x * G; base < p.batch; base += (long long) gridDim.x * G) {
+        const long long item = base + g;
+        const bool valid = item < p.batch;
+        const cf* __restrict__ src = p.in + item * p.in_stride;
+        cf* __restrict__ dst = p.out + item * p.out_stride;
+        cf v[E];
+
+        // ---- stage 0 (Ns = 1, no twiddles) ----
+        if constexpr (MODE == MODE_C2R) {
+            // twist (fft_real_default.cpp:65-111): T[k] = (Y[k] + conj Y[M-k]) + i conj(W_2M^k) (Y[k] - conj Y[M-k]),
+            // computed pairwise: with c = f * diff,  T[k] = sum + c,  T[M-k] = conj(sum - c).
+            static_for<0, E / 2>([&](auto i_) {
+                const int k = j + decltype(i_)::value * T;       // 0 .. M/2-1
+                cf y0 = make_float2(0.f, 0.f), y1 = y0;
+                if (valid) { y0 = ld_stream(src + k); y1 = ld_stream(src + (M - k)); }
+                const cf w = __ldg(p.table + (k << sh_real));    // forward W_2M^k; e = conj(w); f = i e = (w.y, w.x)
+                const cf sum = make_float2(y0.x + y1.x, y0.y - y1.y);
+                const cf dif = make_float2(y0.x - y1.x, y0.y + y1.y);
+                const cf c = cmul(make_float2(w.y, w.x), dif);
+                xb[padidx<LOGPAD>(k)] = make_float2(sum.x + c.x, sum.y + c.y);
+                if (k != 0) xb[padidx<LOGPAD>(M - k)] = make_float2(sum.x - c.x, -(sum.y - c.y));
+            });
+            if (j == 0) {
+                cf y = valid ? ld_stream(src + M / 2) : make_float2(0.f, 0.f);
+                xb[padidx<LOGPAD>(M / 2)] = make_float2(2.0f * y.x, -2.0f * y.y);
+            }
+            group_sync<T>(g);
+            stage_gather<M, T, E, R0, LOGPAD, SRC_XBUF>(v, src, xb, j, valid);
+            group_sync<T>(g);
+        } else {
+            stage_gather<M, T, E, R0, LOGPAD, SRC_GLOBAL>(v, src, xb, j, valid);
+        }
+        stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j);
+        stage_scatter<M, T, E, R0, 1, LOGPAD, DST_XCHG>(v, dst, xb, j, valid);
+        group_sync<T>(g);
+
+        // ---- stage 1 (Ns = R0) ----
+        stage_gather<M, T, E, R1, LOGPAD, SRC_XBUF>(v, src, xb, j, valid);
+        stage_math<T, E, R1, R0, INV, TW_LUT>(v, lut1, p.table, 0, j);
+        if constexpr (C::NSTAGE == 2) {
+            if constexpr (MODE == MODE_R2C) {
+                group_sync<T>(g);
+                stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XNAT>(v, dst, xb, j, valid);
+            } else {
+                stage_scatter<M, T, E, R1, R0, LOGPAD, DST_GLOBAL>(v, dst, xb, j, valid);
+            }
+        } else {
+            group_sync<T>(g);
+            stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XCHG>(v, dst, xb, j, valid);
+            group_sync<T>(g);
+            // ---- stage 2 (Ns = R0*R1) ----
+            constexpr int TW2 = C::LUT2_SMEM ? TW_LUT : TW_TABLE;
+            stage_gather<M, T, E, R2, LOGPAD, SRC_XBUF>(v, src, xb, j, valid);
+            stage_math<T, E, R2, R0 * R1, INV, TW2>(v, lut2, p.table, sh_last, j);
+            if constexpr (MODE == MODE_R2C) {
+                group_sync<T>(g);
+                stage_scatter<M, T, E, R2, R0 * R1, LOGPAD, DST_XNAT>(v, dst, xb, j, valid);
+            } else {
+                stage_scatter<M, T, E, R2, R0 * R1, LOGPAD, DST_GLOBAL>(v, dst, xb, j, valid);
+            }
+        }
+
+        if constexpr (MODE == MODE_R2C) {
+            // split (fft_real_default.cpp:23-62): Y[k] = (Z[k] + conj Z[M-k]) - i W_2M^k (Z[k] - conj Z[M-k]);
+            // pairwise with c = f * diff:  Y[k] = sum - c,  Y[M-k] = conj(sum + c);  Z[M] == Z[0].
+            group_sync<T>(g);
+            static_for<0, E / 2>([&](auto i_) {
+                const int k = j + decltype(i_)::value * T;       // 0 .. M/2-1
+                const cf z0 = xb[padidx<LOGPAD>(k)];
+                const cf z1 = xb[padidx<LOGPAD>((M - k) & (M - 1))];
+                const cf w = __ldg(p.table + (k << sh_real));    // e = W_2M^k; f = i e = (-w.y, w.x)
+                const cf sum = make_float2(z0.x + z1.x, z0.y - z1.y);
+                const cf dif = make_float2(z0.x - z1.x, z0.y + z1.y);
+                const cf c = cmul(make_float2(-w.y, w.x), dif);
+                if (valid) {
+                    st_stream(dst + k, make_float2(sum.x - c.x, sum.y - c.y));
+                    st_stream(dst + (M - k), make_float2(sum.x + c.x, -(sum.y + c.y)));
+                }
+            });
+            if (j == 0 && valid) {
+                const cf z = xb[padidx<LOGPAD>(M / 2)];
+                st_stream(dst + M / 2, make_float2(2.0f * z.x, -2.0f * z.y));
+            }
+        }
+        // the next iteration's first scatter must not overtake this iteration's last gather
+        group_sync<T>(g);
+    }
+}
+
+}  // namespace ckb

@@ -1,0 +1,110 @@
+// fft_regs.cuh -- register-resident radix-2..32 butterflies for sm_100a.
+//
+// Replaces the reference's scalar / NEON butterfly code (src/ckfft/fft_default.cpp:12-266,
+// src/ckfft/fft_neon.cpp:16-256, src/ckfft/math_util.h:17-80).  Nothing here is a port of
+// that recursion: a radix-R transform (R <= 32) lives entirely in one thread's registers as
+// a fully unrolled decimation-in-time network whose twiddles are compile-time immediates,
+// written so that every general butterfly is 6 FFMA (a + w*b, then 2a - (a + w*b)).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ckb {
+
+typedef float2 cf;
+
+template <int V> struct Int { static constexpr int value = V; };
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+    if constexpr (I < N) {
+        f(Int<I>{});
+        static_for<I + 1, N>(static_cast<F&&>(f));
+    }
+}
+
+__host__ __device__ constexpr int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
+
+// reverse the low log2(R) bits of x
+template <int R>
+__host__ __device__ constexpr int bitrev(int x)
+{
+    int r = 0;
+    for (int b = 1; b < R; b <<= 1) { r = (r << 1) | (x & 1); x >>= 1; }
+    return r;
+}
+
+// cos(2*pi*k/32), k any integer, from the first octant + symmetry
+__host__ __device__ constexpr float cos32(int k)
+{
+    constexpr float t[9] = {
+        1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+        0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+        0.19509032201612826785f, 0.0f };
+    k &= 31;
+    if (k > 16) k = 32 - k;
+    return k > 8 ? -t[16 - k] : t[k];
+}
+__host__ __device__ constexpr float sin32(int k) { return cos32(k - 8); }
+
+__device__ __forceinline__ cf cmul(cf a, cf w)
+{
+    return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+}
+
+// (a, b) <- (a + w b, a - w b) with w = exp(-+ 2 pi i K/32), K in [0, 16), sign by INV
+template <int K, bool INV>
+__device__ __forceinline__ void bfly(cf& a, cf& b)
+{
+    static_assert(K >= 0 && K < 16, "DIT twiddles live in the upper half plane");
+    if constexpr (K == 0) {
+        cf s = make_float2(a.x + b.x, a.y + b.y);
+        cf d = make_float2(a.x - b.x, a.y - b.y);
+        a = s; b = d;
+    } else if constexpr (K == 8) {
+        // w = -i (forward) / +i (inverse):  w b = (b.y, -b.x) / (-b.y, b.x)
+        cf s, d;
+        if constexpr (!INV) { s = make_float2(a.x + b.y, a.y - b.x); d = make_float2(a.x - b.y, a.y + b.x); }
+        else                { s = make_float2(a.x - b.y, a.y + b.x); d = make_float2(a.x + b.y, a.y - b.x); }
+        a = s; b = d;
+    } else if constexpr (K == 4 || K == 12) {
+        // w = c (+-1 -+ i) : two adds, then four FFMA with the immediate c
+        constexpr float c = 0.70710678118654752440f;
+        float p, q;   // w b = c * (p, q)
+        if constexpr (K == 4) {
+            if constexpr (!INV) { p = b.x + b.y; q = b.y - b.x; } else { p = b.x - b.y; q = b.x + b.y; }
+        } else {
+            if constexpr (!INV) { p = b.y - b.x; q = -(b.x + b.y); } else { p = -(b.x + b.y); q = b.x - b.y; }
+        }
+        cf s = make_float2(fmaf(c, p, a.x), fmaf(c, q, a.y));
+        cf d = make_float2(fmaf(-c, p, a.x), fmaf(-c, q, a.y));
+        a = s; b = d;
+    } else {
+        constexpr float wr = cos32(K);
+        constexpr float wi = INV ? sin32(K) : -sin32(K);
+        cf s = make_float2(fmaf(wr, b.x, fmaf(-wi, b.y, a.x)), fmaf(wr, b.y, fmaf(wi, b.x, a.y)));
+        cf d = make_float2(fmaf(2.0f, a.x, -s.x), fmaf(2.0f, a.y, -s.y));
+        a = s; b = d;
+    }
+}
+
+// In-register DFT of R points held in v[OFF .. OFF+R).  Input sample t must sit in slot
+// OFF + bitrev<R>(t); output bin u is left in slot OFF + u.
+template <int R, int OFF, bool INV, int E>
+__device__ __forceinline__ void fft_regs(cf (&v)[E])
+{
+    static_assert(R >= 1 && R <= 32 && (R & (R - 1)) == 0, "radix must be a power of two <= 32");
+    static_for<1, ilog2(R) + 1>([&](auto s_) {
+        constexpr int len = 1 << decltype(s_)::value;
+        constexpr int half = len / 2;
+        static_for<0, R / len>([&](auto b_) {
+            constexpr int base = OFF + decltype(b_)::value * len;
+            static_for<0, half>([&](auto k_) {
+                constexpr int k = decltype(k_)::value;
+                bfly<k * (32 / len), INV>(v[base + k], v[base + k + half]);
+            });
+        });
+    });
+}
+
+}  // namespace ckb

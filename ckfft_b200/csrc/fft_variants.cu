@@ -1,0 +1,68 @@
+// fft_variants.cu -- instantiates the single-pass kernel family for ONE (direction, mode) variant.
+// Compiled four times (-DCKB_VARIANT=0..3) so the heavy template instantiations build in parallel:
+//   0  complex forward   (CkFftComplexForward,  reference src/ckfft/ckfft.cpp:78-95)
+//   1  complex inverse   (CkFftComplexInverse,  :97-114)
+//   2  real forward      (CkFftRealForward,     :36-53)   half-length forward FFT + fused split
+//   3  real inverse      (CkFftRealInverse,     :55-76)   fused twist + half-length inverse FFT
+#include "launch.h"
+#include "plans.h"
+
+#ifndef CKB_VARIANT
+#error "compile with -DCKB_VARIANT=0..3"
+#endif
+
+namespace ckb {
+
+#if CKB_VARIANT == 0
+#define CKB_FN launch_c2c_fwd
+static constexpr bool kInv = false; static constexpr int kMode = MODE_C2C;
+#elif CKB_VARIANT == 1
+#define CKB_FN launch_c2c_inv
+static constexpr bool kInv = true; static constexpr int kMode = MODE_C2C;
+#elif CKB_VARIANT == 2
+#define CKB_FN launch_r2c
+static constexpr bool kInv = false; static constexpr int kMode = MODE_R2C;
+#else
+#define CKB_FN launch_c2r
+static constexpr bool kInv = true; static constexpr int kMode = MODE_C2R;
+#endif
+
+template <class C>
+static cudaError_t launch_cfg(const KernelParams& p, cudaStream_t s)
+{
+    // persistent grid: as many CTAs as fit on the device at once (a multiple of the SM count),
+    // or fewer when the batch is small.  Cached per device.
+    static int grid_cap[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (grid_cap[dev] == 0) {
+        e = cudaFuncSetAttribute(fft_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_kernel<C>, C::THREADS, C::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        grid_cap[dev] = occ * sm_count_of_current_device();
+    }
+    const long long ctas = (p.batch + C::G - 1) / C::G;
+    const int grid = (int) (ctas < grid_cap[dev] ? ctas : grid_cap[dev]);
+    if (grid <= 0) return cudaSuccess;
+    fft_kernel<C><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
+{
+    switch (M) {
+#define X(M_, E_, R0_, R1_, R2_, G_, MINB_) \
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_>>(p, s);
+        CKB_SINGLE_PASS_PLANS(X)
+#undef X
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace ckb
