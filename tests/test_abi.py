@@ -1,0 +1,134 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports exactly what include/*.h declare,
+the headers are valid C, and the host-side logic that needs no GPU (argument checks, the size-query
+protocol of CkFftInit, the launch planner) behaves like the reference (src/ckfft/ckfft.cpp:14-34,
+src/ckfft/context.cpp:27-51).  No compute calls here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import ckfft_b200 as ck
+from ckfft_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INC = os.path.join(ROOT, "include")
+
+
+def declared_functions(header):
+    text = open(os.path.join(INC, "ckfft", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"\b(CkFft\w+)\s*\(", text))
+
+
+def exported_symbols():
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    return {line.split()[-1] for line in out.splitlines() if " T " in line}
+
+
+def test_library_exports_every_declared_symbol():
+    declared = declared_functions("ckfft.h") | declared_functions("ckfft_b200.h")
+    assert declared == set(_lib.CLASSIC_SYMBOLS) | set(_lib.B200_SYMBOLS)
+    exported = exported_symbols()
+    missing = declared - exported
+    assert not missing, f"declared but not exported: {missing}"
+    extra = {s for s in exported if s.startswith("CkFft")} - declared
+    assert not extra, f"exported but not declared: {extra}"
+
+
+def test_classic_header_is_the_reference_surface():
+    """the six functions of inc/ckfft/ckfft.h:59-158, nothing more"""
+    assert declared_functions("ckfft.h") == {"CkFftInit", "CkFftRealForward", "CkFftRealInverse",
+                                             "CkFftComplexForward", "CkFftComplexInverse", "CkFftShutdown"}
+
+
+@pytest.mark.parametrize("header", ["ckfft.h", "ckfft_b200.h"])
+def test_headers_are_valid_c(header, tmp_path):
+    """the reference keeps its header C-clean with src/test/test.c; same check here"""
+    src = tmp_path / "t.c"
+    src.write_text(f'#include "ckfft/{header}"\nint main(void) {{ CkFftComplex c; c.real = 0; c.imag = 0; return (int) c.real; }}\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", f"-I{INC}", str(src)])
+
+
+def test_python_binding_loads():
+    lib = _lib.load()
+    for name in _lib.CLASSIC_SYMBOLS + _lib.B200_SYMBOLS:
+        assert hasattr(lib, name)
+    assert isinstance(ck.kernel_launches(), int)
+
+
+def test_init_argument_checks():
+    """src/ckfft/ckfft.cpp:16-31: every invalid argument gives NULL before anything else happens."""
+    lib = _lib.load()
+    for nmax in (0, -4, 3, 1000, -(2 ** 31)):
+        assert not lib.CkFftInit(nmax, ck.BOTH, None, None)
+    for direction in (0, 4, 7, -1):
+        assert not lib.CkFftInit(1024, direction, None, None)
+    buf = C.create_string_buffer(1 << 20)
+    assert not lib.CkFftInit(1024, ck.BOTH, buf, None)      # buf without bufSize
+    assert ck.last_error() != ""
+
+
+def test_size_query_protocol():
+    """src/ckfft/context.cpp:47-51 and the usage in inc/ckfft/ckfft.h:51-55: a NULL or too-small buffer
+    makes CkFftInit write the required size and return NULL."""
+    lib = _lib.load()
+    sizes = {}
+    for direction in (ck.FORWARD, ck.INVERSE, ck.BOTH):
+        sz = C.c_size_t(0)
+        assert not lib.CkFftInit(1024, direction, None, C.byref(sz))
+        assert sz.value > 0
+        sizes[direction] = sz.value
+        small = C.create_string_buffer(16)
+        sz2 = C.c_size_t(16)
+        assert not lib.CkFftInit(1024, direction, small, C.byref(sz2))
+        assert sz2.value == sz.value
+    # one table per requested direction, 8 bytes per entry (context.cpp:34-45)
+    assert sizes[ck.FORWARD] == sizes[ck.INVERSE]
+    assert sizes[ck.BOTH] - sizes[ck.FORWARD] == 1024 * 8
+
+
+def test_transform_calls_reject_null_context():
+    lib = _lib.load()
+    buf = C.create_string_buffer(64)
+    assert lib.CkFftComplexForward(None, 4, buf, buf) == 0
+    assert lib.CkFftRealInverse(None, 4, buf, buf, None) == 0
+    assert lib.CkFftComplexForwardBatch(None, 4, buf, buf, 1) == 0
+    lib.CkFftShutdown(None)   # NULL-safe like the reference (context.cpp:116-122)
+
+
+def test_planner_covers_every_power_of_two():
+    for lg in range(0, 15):
+        n = 1 << lg
+        p = ck.get_plan(n, real=False)
+        assert p is not None and p["complex_points"] == n
+        prod = 1
+        for r in p["radix"][0]:
+            prod *= r
+        assert prod == n, p
+        assert p["passes"] == 1
+        assert p["threads_per_transform"] * p["elems_per_thread"] == n
+        assert p["shared_bytes"] <= 227 * 1024
+        q = ck.get_plan(2 * n, real=True)
+        assert q is not None and q["complex_points"] == n
+    assert ck.get_plan(24) is None and ck.get_plan(0) is None
+    # the headline shapes: one warp per 1024-point transform, 32x32 radix split, 4 transforms per CTA
+    p = ck.get_plan(1024)
+    assert p["radix"] == [[32, 32]] and p["threads_per_transform"] == 32 and p["elems_per_thread"] == 32
+    q = ck.get_plan(4096, real=True)
+    assert q["complex_points"] == 2048
+
+
+def test_no_gpu_fails_loudly():
+    """Without a usable GPU the product must not compute anything: CkFftInit -> NULL with a reason."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    with pytest.raises(ck.CkFftError) as e:
+        ck.Context(1024)
+    assert "no CPU path" in str(e.value)

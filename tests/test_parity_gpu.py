@@ -1,0 +1,309 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (host pointers and device pointers),
+against the oracle restatement, the committed golden vectors of the reference, fp64 truth and
+size-independent properties at BASELINE.json's full sizes.
+
+Tolerance (BASELINE.json north_star): relative RMS error <= 1e-6 * log2(N), written in conftest.tolerance.
+"""
+import ctypes as C
+import threading
+
+import numpy as np
+import pytest
+
+import ckfft_b200 as ck
+import oracle
+from ckfft_b200 import _lib
+from conftest import rel_rms, tolerance, uniform_complex
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+ALL_SIZES = [1 << k for k in range(0, 15)]            # complex 1 .. 16384 (single pass)
+REAL_SIZES = [1 << k for k in range(0, 16)]           # real 1 .. 32768
+
+
+def harness_rms(a, b):
+    d = (np.asarray(a, np.complex64) - np.asarray(b, np.complex64)).view(np.float32)
+    return float(np.sqrt(np.sum(d.astype(np.float64) ** 2) / d.size))
+
+
+@pytest.fixture(scope="module")
+def ctx_big():
+    c = ck.Context(32768, ck.BOTH)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def orc_big():
+    o = oracle.Restatement(32768, 3)
+    yield o
+    o.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle parity, every size, host path and device path, awkward batch counts
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", ALL_SIZES)
+@pytest.mark.parametrize("inverse", [False, True])
+def test_complex_vs_oracle(ctx_big, orc_big, n, inverse):
+    rng = np.random.default_rng(n + inverse)
+    for batch in (1, 3, 37):
+        if n * batch > (1 << 19):
+            continue
+        x = uniform_complex(rng, (batch, n))
+        want = orc_big.complex(x, inverse)
+        f = ctx_big.complex_inverse if inverse else ctx_big.complex_forward
+        got_host = f(x)
+        got_dev = f(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert np.array_equal(got_host.view(np.uint32), got_dev.view(np.uint32)), "host and device paths differ"
+        assert rel_rms(got_host, want) <= tolerance(n), (n, batch)
+        assert rel_rms(got_host, oracle.fp64_c2c(x, inverse)) <= tolerance(n)
+
+
+@pytest.mark.parametrize("n", REAL_SIZES)
+def test_real_vs_oracle(ctx_big, orc_big, n):
+    rng = np.random.default_rng(1000 + n)
+    for batch in (1, 2, 3, 33):
+        if n * batch > (1 << 19):
+            continue
+        x = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+        want = orc_big.real_forward(x)
+        got = ctx_big.real_forward(x)
+        got_dev = ctx_big.real_forward(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), got_dev.view(np.uint32))
+        assert rel_rms(got, want) <= tolerance(n), (n, batch)
+        assert rel_rms(got, oracle.fp64_real_forward(x)) <= tolerance(n)
+        # inverse on the oracle's spectrum, and on a generic (non-Hermitian-edge) spectrum: the imaginary
+        # parts of bins 0 and n/2 are NOT ignored by the reference (fft_real_default.cpp:79-107)
+        for spec in (want, uniform_complex(rng, want.shape)):
+            want_inv = orc_big.real_inverse(spec, n)
+            got_inv = ctx_big.real_inverse(spec, n)
+            got_inv_dev = ctx_big.real_inverse(torch.from_numpy(spec).cuda(), n).cpu().numpy()
+            assert np.array_equal(got_inv.view(np.uint32), got_inv_dev.view(np.uint32))
+            assert rel_rms(got_inv, want_inv) <= tolerance(n), (n, batch)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own fixture and acceptance criteria (golden vectors generated from the reference)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1 << k for k in range(0, 13)])
+@pytest.mark.parametrize("nmax", ["n", 8192])
+def test_golden_fixture(golden, n, nmax):
+    """src/test/test.cpp:866-921: counts 4096 .. 1 of input.txt, contexts with maxCount == count and
+    maxCount == 2*4096.  Checked three ways: north_star tolerance vs the reference's outputs, the
+    harness's absolute RMS <= 0.001 vs KISS FFT, and the harness's real-vs-complex self-consistency."""
+    nmax = n if nmax == "n" else nmax
+    x = golden["input"][:n]
+    with ck.Context(max(nmax, 1), ck.BOTH) as ctx:
+        f, i = ctx.complex_forward(x), ctx.complex_inverse(x)
+        assert rel_rms(f, golden[f"cfwd_{n}"]) <= tolerance(n)
+        assert rel_rms(i, golden[f"cinv_{n}"]) <= tolerance(n)
+        assert harness_rms(f, golden[f"kfwd_{n}"]) <= 1e-3
+        assert harness_rms(i, golden[f"kinv_{n}"]) <= 1e-3
+        xr = np.ascontiguousarray(x.real)
+        rf = ctx.real_forward(xr)
+        assert rel_rms(rf, golden[f"rfwd_{n}"]) <= tolerance(n)
+        k = n // 2 + 1
+        cref = ctx.complex_forward(xr.astype(np.complex64))
+        assert harness_rms(rf * np.float32(0.5), cref[:k]) <= 1e-3
+        ri = ctx.real_inverse(np.ascontiguousarray(cref[:k]), n)
+        assert rel_rms(ri, golden[f"rinv_{n}"]) <= tolerance(n)
+        d = ri[:k] - ctx.complex_inverse(cref)[:k].real
+        assert float(np.sqrt(np.mean(d.astype(np.float64) ** 2))) <= 1e-3
+
+
+def test_table_stride_contexts_are_bit_identical(golden):
+    """A larger nMax only changes the table stride (fft.cpp:35); results must not change at all."""
+    x = golden["input"][:1024]
+    outs = []
+    for nmax in (1024, 2048, 8192, 1 << 16):
+        with ck.Context(nmax, ck.BOTH) as ctx:
+            outs.append((ctx.complex_forward(x), ctx.real_forward(np.ascontiguousarray(x.real))))
+    for a, b in outs[1:]:
+        assert np.array_equal(a.view(np.uint32), outs[0][0].view(np.uint32))
+        assert np.array_equal(b.view(np.uint32), outs[0][1].view(np.uint32))
+
+
+def test_example_round_trip(golden):
+    """src/example/main.cpp:44-84"""
+    x = golden["example_in"]
+    with ck.Context(1024, ck.BOTH) as ctx:
+        f = ctx.real_forward(x)
+        assert rel_rms(f, golden["example_fwd"]) <= tolerance(1024)
+        rt = ctx.real_inverse(f, 1024)
+        assert float(np.sum((rt / 2048.0 - x) ** 2)) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# properties at BASELINE.json's full sizes (device resident)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_c2c_1024_x_1M_round_trip_and_spot_parity(orc_big):
+    """config 2: N=1024 x 2^20 transforms.  inverse(forward(x)) = N x on every transform; Parseval on
+    every transform; 4096 leading + 4096 random transforms against the oracle."""
+    n, batch = 1024, 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.empty((batch, n, 2), dtype=torch.float32, device="cuda")
+    x.uniform_(-1, 1, generator=g)
+    x = torch.view_as_complex(x)
+    with ck.Context(n, ck.BOTH) as ctx:
+        y = ctx.complex_forward(x)
+        energy_in = (x.real.double() ** 2 + x.imag.double() ** 2).sum(dim=1)
+        energy_out = (y.real.double() ** 2 + y.imag.double() ** 2).sum(dim=1)
+        assert float(((energy_out / n - energy_in).abs() / energy_in).max()) < 1e-5
+        idx = torch.cat([torch.arange(4096, device="cuda"),
+                         torch.randint(0, batch, (4096,), device="cuda", generator=g)])
+        xs, ys = x[idx].cpu().numpy(), y[idx].cpu().numpy()
+        assert rel_rms(ys, orc_big.complex(xs, False)) <= tolerance(n)
+        assert rel_rms(ys, oracle.fp64_c2c(xs, False)) <= tolerance(n)
+        z = ctx.complex_inverse(y)
+        del y
+        err = torch.linalg.vector_norm((z / n - x).view(batch, -1).abs().double(), dim=1)
+        ref = torch.linalg.vector_norm(x.view(batch, -1).abs().double(), dim=1)
+        assert float((err / ref).max()) <= tolerance(n)
+    torch.cuda.synchronize()
+
+
+def test_full_size_r2c_4096_x_256K_round_trip_and_spot_parity(orc_big):
+    """config 3: N=4096 real x 2^18 frames, R2C then C2R = 2N x; forward scale 2; spot parity."""
+    n, batch = 4096, 1 << 18
+    g = torch.Generator(device="cuda").manual_seed(1235)
+    x = torch.empty((batch, n), dtype=torch.float32, device="cuda")
+    x.uniform_(-1, 1, generator=g)
+    with ck.Context(n, ck.BOTH) as ctx:
+        y = ctx.real_forward(x)
+        assert y.shape == (batch, n // 2 + 1)
+        # DC bin = 2 * sum(x), imaginary parts of DC and Nyquist are exactly zero-sum rounding
+        dc = 2.0 * x.double().sum(dim=1)
+        assert float((y[:, 0].real.double() - dc).abs().max()) < 1e-2
+        idx = torch.randint(0, batch, (2048,), device="cuda", generator=g)
+        xs, ys = x[idx].cpu().numpy(), y[idx].cpu().numpy()
+        assert rel_rms(ys, orc_big.real_forward(xs)) <= tolerance(n)
+        assert rel_rms(ys, oracle.fp64_real_forward(xs)) <= tolerance(n)
+        z = ctx.real_inverse(y, n)
+        err = torch.linalg.vector_norm((z / (2.0 * n) - x).double(), dim=1)
+        ref = torch.linalg.vector_norm(x.double(), dim=1)
+        assert float((err / ref).max()) <= tolerance(n)
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("n", [16, 256, 4096, 16384])
+def test_linearity_and_impulse(ctx_big, n):
+    rng = np.random.default_rng(n)
+    a, b = uniform_complex(rng, (4, n)), uniform_complex(rng, (4, n))
+    fa, fb = ctx_big.complex_forward(a), ctx_big.complex_forward(b)
+    fab = ctx_big.complex_forward((a + np.complex64(2) * b).astype(np.complex64))
+    assert rel_rms(fab, fa + 2 * fb) <= 2 * tolerance(n)
+    imp = np.zeros((1, n), np.complex64); imp[0, 1] = 1
+    k = np.arange(n)
+    assert np.allclose(ctx_big.complex_forward(imp)[0], np.exp(-2j * np.pi * k / n), atol=1e-6)
+    assert np.allclose(ctx_big.complex_inverse(imp)[0], np.exp(+2j * np.pi * k / n), atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# error behaviour of the boundary (reference: src/ckfft/ckfft.cpp:36-114)
+# ---------------------------------------------------------------------------------------------
+def test_error_returns():
+    lib = _lib.load()
+    fwd = ck.Context(64, ck.FORWARD)
+    inv = ck.Context(64, ck.INVERSE)
+    a = np.zeros(64, np.complex64); b = np.zeros(64, np.complex64)
+    pa, pb = a.ctypes.data, b.ctypes.data
+    assert lib.CkFftComplexForward(fwd.handle, 64, pa, pb) == 1
+    assert lib.CkFftComplexInverse(fwd.handle, 64, pa, pb) == 0        # wrong direction
+    assert lib.CkFftComplexForward(inv.handle, 64, pa, pb) == 0
+    assert lib.CkFftRealForward(inv.handle, 64, pa, pb) == 0
+    assert lib.CkFftComplexInverse(inv.handle, 64, pa, pb) == 1
+    assert lib.CkFftComplexForward(fwd.handle, 128, pa, pb) == 0        # n > nMax
+    assert lib.CkFftComplexForward(fwd.handle, 48, pa, pb) == 0         # not a power of two
+    assert lib.CkFftComplexForward(fwd.handle, 0, pa, pb) == 0
+    assert lib.CkFftComplexForward(fwd.handle, -64, pa, pb) == 0
+    assert lib.CkFftComplexForward(fwd.handle, -(2 ** 31), pa, pb) == 0  # the reference's INT_MIN hole
+    assert lib.CkFftComplexForward(fwd.handle, 64, pa, pa) == 0         # in == out
+    assert lib.CkFftComplexForward(fwd.handle, 64, None, pb) == 0
+    assert lib.CkFftComplexForward(fwd.handle, 64, pa, None) == 0
+    assert lib.CkFftRealInverse(inv.handle, 64, pa, pb, None) == 0      # tmpBuf NULL (ckfft.cpp:57-60)
+    assert lib.CkFftRealInverse(inv.handle, 64, pa, pb, pa) == 1
+    assert lib.CkFftRealInverseBatch(inv.handle, 64, pa, pb, None, 1) == 1   # batched variant ignores tmpBuf
+    assert lib.CkFftComplexForwardBatch(fwd.handle, 16, pa, pb, 0) == 1      # empty batch is a no-op
+    # device pointer + host pointer mixed, and a misaligned device pointer
+    d = torch.zeros(130, dtype=torch.complex64, device="cuda")
+    assert lib.CkFftComplexForward(fwd.handle, 64, d.data_ptr(), pb) == 0
+    assert lib.CkFftComplexForwardBatchAsync(fwd.handle, 64, d.data_ptr() + 4, d.data_ptr() + 8 * 64, 1, 0, 0, None) == 0
+    assert lib.CkFftComplexForwardBatchAsync(fwd.handle, 64, d.data_ptr(), d.data_ptr() + 8 * 64, 1, 32, 0, None) == 0  # stride < n
+    assert ck.last_error() != ""
+    fwd.close(); inv.close()
+
+
+def test_user_buffer_context(golden):
+    """CkFftInit with caller storage (inc/ckfft/ckfft.h:51-55): the context lives in the caller's buffer and
+    CkFftShutdown does not free it (context.cpp:111,116-122)."""
+    lib = _lib.load()
+    sz = C.c_size_t(0)
+    assert not lib.CkFftInit(256, ck.BOTH, None, C.byref(sz))
+    buf = C.create_string_buffer(sz.value)
+    h = lib.CkFftInit(256, ck.BOTH, buf, C.byref(sz))
+    assert h == C.addressof(buf)
+    x = np.ascontiguousarray(golden["input"][:256]); out = np.empty_like(x)
+    assert lib.CkFftComplexForward(h, 256, x.ctypes.data, out.ctypes.data) == 1
+    assert rel_rms(out, golden["cfwd_256"]) <= tolerance(256)
+    lib.CkFftShutdown(h)
+    buf.raw   # still ours
+
+
+def test_strided_async(ctx_big, orc_big):
+    """stream-ordered variant with padded strides (aligned spectrum stride for R2C)."""
+    lib = _lib.load()
+    n, batch = 1024, 9
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, (batch, n + 8)).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.zeros((batch, n // 2 + 2), dtype=torch.complex64, device="cuda")   # padded: 514 bins per row
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ok = lib.CkFftRealForwardBatchAsync(ctx_big.handle, n, xd.data_ptr(), yd.data_ptr(), batch, n + 8, n // 2 + 2, s.cuda_stream)
+    assert ok == 1
+    s.synchronize()
+    want = orc_big.real_forward(np.ascontiguousarray(x[:, :n]))
+    got = yd.cpu().numpy()
+    assert rel_rms(got[:, : n // 2 + 1], want) <= tolerance(n)
+    assert np.all(got[:, n // 2 + 1] == 0)     # padding untouched
+    xo = torch.zeros((batch, n + 2), dtype=torch.float32, device="cuda")
+    ok = lib.CkFftRealInverseBatchAsync(ctx_big.handle, n, yd.data_ptr(), xo.data_ptr(), batch, n // 2 + 2, n + 2, None)
+    assert ok == 1
+    torch.cuda.synchronize()
+    assert rel_rms(xo.cpu().numpy()[:, :n], 2.0 * n * x[:, :n]) <= tolerance(n)
+
+
+def test_context_shared_between_threads(orc_big):
+    """'contexts can be used simultaneously on different threads' (inc/ckfft/ckfft.h:39-41)"""
+    ctx = ck.Context(2048, ck.BOTH)
+    rng = np.random.default_rng(11)
+    xs = [uniform_complex(rng, (17, 2048)) for _ in range(4)]
+    want = [orc_big.complex(x) for x in xs]
+    errs = [None] * 4
+
+    def work(i):
+        for _ in range(5):
+            errs[i] = rel_rms(ctx.complex_forward(xs[i]), want[i])
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert all(e is not None and e <= tolerance(2048) for e in errs), errs
+    ctx.close()
+
+
+def test_large_host_batch_is_chunked(orc_big):
+    """host path with more data than one staging chunk (3 chunks in flight, api.cu run_host)"""
+    n, batch = 4096, 3000          # 98 MB in, > 32 MiB chunk
+    rng = np.random.default_rng(2)
+    x = uniform_complex(rng, (batch, n))
+    with ck.Context(n, ck.FORWARD) as ctx:
+        before = ck.kernel_launches()
+        y = ctx.complex_forward(x)
+        assert ck.kernel_launches() - before >= 3
+    pick = [0, 1, 1023, 1024, 1025, 2047, 2048, 2999]
+    assert rel_rms(y[pick], orc_big.complex(x[pick])) <= tolerance(n)
+    assert rel_rms(y[::97], oracle.fp64_c2c(x[::97])) <= tolerance(n)
