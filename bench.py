@@ -1,0 +1,410 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline benchmark of BASELINE.json:
+"Batched fp32 C2C FFT HBM GB/s + 5N*log2N GFLOP/s at N=1024, 1/2/4/8 B200".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+One "step" = one pass of the hot path over one batch: CkFftComplexForward on 2^20 transforms of
+N=1024 (config[1] of BASELINE.json; 8.59 GB in + 8.59 GB out per GPU, far larger than the 126 MB L2,
+so no L2 flush is needed between iterations).  With N>1 GPUs (launched under torchrun, one rank per
+GPU) every rank runs the same per-GPU batch (weak scaling, independent transforms, no collective on
+the data path); `value` is the work of all ranks divided by the slowest rank's device time.
+
+One JSON line on stdout (rank 0):
+  value / ms_per_step   device-resident throughput, CUDA events on the launching stream, max over ranks
+  e2e                   same metric through the C ABI with pinned HOST buffers (CkFftComplexForwardBatch:
+                        chunked H2D -> kernel -> D2H inside the timed region)
+  roofline              algorithmic bytes / kernel time vs the measured HBM copy peak
+  cpu_baseline          the reference ckfft (oracle/_ref, compiled unmodified) on this box's host cores
+  clocks                nvidia-smi samples taken while the steps ran
+`--impl reference` times the reference CPU implementation instead (rank 0 only), same metric/config.
+Other workloads (`--workload r2c4096|c2r4096|c2c<N>`) exist for the parity configs and the size sweep;
+the default is the judged one.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Batched fp32 C2C FFT HBM GB/s + 5N*log2N GFLOP/s at N=1024"
+FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+# ---------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------
+def workload_spec(name: str):
+    """-> dict(kind, n, batch, bytes_per_transform, flops_per_transform, description)"""
+    if name == "c2c1024":
+        n, batch, kind = 1024, 1 << 20, "c2c"
+    elif name == "r2c4096":
+        n, batch, kind = 4096, 1 << 18, "r2c"
+    elif name == "c2r4096":
+        n, batch, kind = 4096, 1 << 18, "c2r"
+    elif name.startswith("c2c"):
+        n, kind = int(name[3:]), "c2c"
+        batch = max(1, (1 << 28) // n)          # config 4: constant 2 GiB in + 2 GiB out
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    if kind == "c2c":
+        nbytes, flops = 16 * n, 5.0 * n * np.log2(n)
+    else:
+        nbytes, flops = 4 * n + 8 * (n // 2 + 1), 2.5 * n * np.log2(n)
+    desc = {"c2c": f"batched complex C2C forward N={n} x {batch} transforms fp32 per GPU",
+            "r2c": f"batched real R2C N={n} x {batch} frames fp32 per GPU",
+            "c2r": f"batched real C2R N={n} x {batch} frames fp32 per GPU"}[kind]
+    return dict(name=name, kind=kind, n=n, batch=batch, bytes=nbytes, flops=flops, desc=desc)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, device copy)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(name):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get(name)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, gpu_index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = []
+        with open(self.tmp.name) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) >= 7:
+                    try:
+                        rows.append((float(parts[0]), float(parts[1]), float(parts[2]), parts[3:7]))
+                    except ValueError:
+                        pass
+        os.unlink(self.tmp.name)
+        if not rows:
+            return out
+        # "under load": samples drawing more than half of the largest power seen
+        pmax = max(r[2] for r in rows)
+        loaded = [r for r in rows if r[2] >= 0.5 * pmax] or rows
+        out["sm_mhz"] = statistics.median(r[0] for r in loaded)
+        out["sm_max_mhz"] = max(r[1] for r in rows)
+        out["power_w_max"] = pmax
+        out["samples"] = len(loaded)
+        out["reasons"] = [n for i, n in enumerate(self.NAMES) if any(r[3][i].lower() == "active" for r in loaded)]
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference (oracle/_ref): the cpu_baseline leg and the --impl reference arm
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(spec, n_transforms, threads, repeats=1, seed=1234, min_seconds=0.0):
+    """Time the reference ckfft (unmodified, compiled by oracle/build.py) on `n_transforms` transforms.
+    Returns (best seconds, kind)."""
+    import oracle
+
+    n, kind = spec["n"], spec["kind"]
+    rng = np.random.default_rng(seed)
+
+    def rand_c64(rows, cols):
+        return (rng.random((rows, cols, 2), dtype=np.float32) * np.float32(2) - np.float32(1)).view(np.complex64)[..., 0]
+    if oracle.reference_available():
+        impl, tag = oracle.Reference(n, 3), "reference"
+    else:   # the compiled reference did not travel: time our bit-identical C port instead
+        impl, tag = oracle.Restatement(n, 3), "port"
+    if kind == "c2c":
+        x = rand_c64(n_transforms, n)
+        out = np.empty_like(x)
+        run = (lambda: impl.complex(x, False, threads, out)) if tag == "reference" else (lambda: impl.complex(x, False))
+    elif kind == "r2c":
+        x = rng.random((n_transforms, n), dtype=np.float32) * np.float32(2) - np.float32(1)
+        out = np.empty((n_transforms, n // 2 + 1), np.complex64)
+        run = (lambda: impl.real_forward(x, threads, out)) if tag == "reference" else (lambda: impl.real_forward(x))
+    else:
+        x = rand_c64(n_transforms, n // 2 + 1)
+        out = np.empty((n_transforms, n), np.float32)
+        run = (lambda: impl.real_inverse(x, n, threads, out)) if tag == "reference" else (lambda: impl.real_inverse(x, n))
+    run()   # touch pages, warm caches
+    best = float("inf")
+    spent, done = 0.0, 0
+    while done < repeats or (spent < min_seconds and done < 200):
+        t = time.perf_counter()
+        run()
+        dt = time.perf_counter() - t
+        best = min(best, dt)
+        spent += dt
+        done += 1
+    impl.close()
+    return best, tag
+
+
+def cpu_baseline(spec):
+    """Bounded sample on the host cores: all threads and one thread, best of 3."""
+    cores = os.cpu_count() or 1
+    sample_all = min(spec["batch"], 1 << 18)
+    sample_one = min(spec["batch"], 1 << 14)
+    t_all, tag = cpu_reference_run(spec, sample_all, 0, repeats=3, min_seconds=6.0)
+    t_one, _ = cpu_reference_run(spec, sample_one, 1, repeats=3, min_seconds=3.0)
+    gbs_all = spec["bytes"] * sample_all / t_all / 1e9
+    gbs_one = spec["bytes"] * sample_one / t_one / 1e9
+    return {"value": round(gbs_all, 3), "unit": "GB/s", "cores": cores, "kind": tag,
+            "sample": f"{sample_all} of {spec['batch']} transforms (same seeded uniform(-1,1) data), OpenMP over "
+                      f"the batch on {cores} host threads, one shared context, best pass of >= 6 s of repeats",
+            "gflops": round(spec["flops"] * sample_all / t_all / 1e9, 2),
+            "us_per_transform": round(t_all / sample_all * 1e6, 4),
+            "single_core": {"value": round(gbs_one, 3), "unit": "GB/s", "us_per_transform": round(t_one / sample_one * 1e6, 3),
+                            "sample": f"{sample_one} transforms, 1 thread"}}
+
+
+def run_reference_arm(args, spec, rank):
+    """--impl reference: the reference's own CPU implementation, all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # size one step so that (steps + warmup) steps take about a minute in total
+    probe = 1 << 12
+    t_probe, tag = cpu_reference_run(spec, probe, 0, repeats=2)
+    per_transform = t_probe / probe
+    budget = 60.0 / max(1, args.steps + args.warmup)
+    sample = int(min(spec["batch"], max(1 << 10, budget / per_transform)))
+    sample = 1 << (sample.bit_length() - 1)
+    import oracle
+
+    n = spec["n"]
+    impl = oracle.Reference(n, 3) if oracle.reference_available() else oracle.Restatement(n, 3)
+    rng = np.random.default_rng(1234)
+    x = (rng.random((sample, n, 2), dtype=np.float32) * np.float32(2) - np.float32(1)).view(np.complex64)[..., 0]
+    if spec["kind"] == "r2c":
+        xin, out = np.ascontiguousarray(x.real), np.empty((sample, n // 2 + 1), np.complex64)
+        step = (lambda: impl.real_forward(xin, 0, out)) if tag == "reference" else (lambda: impl.real_forward(xin))
+    elif spec["kind"] == "c2r":
+        xin, out = np.ascontiguousarray(x[:, : n // 2 + 1]), np.empty((sample, n), np.float32)
+        step = (lambda: impl.real_inverse(xin, n, 0, out)) if tag == "reference" else (lambda: impl.real_inverse(xin, n))
+    else:
+        out = np.empty_like(x)
+        step = (lambda: impl.complex(x, False, 0, out)) if tag == "reference" else (lambda: impl.complex(x, False))
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    impl.close()
+    gbs = spec["bytes"] * sample / dt / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "gflops": round(spec["flops"] * sample / dt / 1e9, 2),
+        "config": {"workload": spec["desc"], "n": n, "kind": spec["kind"],
+                   "step": f"bounded sample: {sample} transforms per step on the host CPU"},
+        "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": cores, "kind": tag,
+                         "sample": f"{sample} transforms per step, OpenMP over the batch on {cores} host threads"},
+        "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2c1024")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    spec = workload_spec(args.workload)
+
+    if args.impl == "reference":
+        run_reference_arm(args, spec, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import ckfft_b200 as ck
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    n, batch, kind = spec["n"], spec["batch"], spec["kind"]
+    ctx = ck.Context(n, ck.BOTH)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    if kind == "c2c":
+        x = torch.view_as_complex(torch.empty((batch, n, 2), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g))
+        y = torch.empty_like(x)
+        step = lambda: ctx.complex_forward(x, y)   # noqa: E731
+    elif kind == "r2c":
+        x = torch.empty((batch, n), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g)
+        y = torch.empty((batch, n // 2 + 1), dtype=torch.complex64, device=dev)
+        step = lambda: ctx.real_forward(x, y)      # noqa: E731
+    else:
+        x = torch.view_as_complex(torch.empty((batch, n // 2 + 1, 2), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g))
+        y = torch.empty((batch, n), dtype=torch.float32, device=dev)
+        step = lambda: ctx.real_inverse(x, n, y)   # noqa: E731
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = ck.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    launches = ck.kernel_launches() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    gbs = spec["bytes"] * batch * world / ms_step / 1e6
+    gflops = spec["flops"] * batch * world / ms_step / 1e6
+
+    # cheap in-run sanity check of the timed buffers (full parity lives in tests/): Parseval on a slice
+    if kind == "c2c":
+        xin, yout = x[:64], y[:64]
+        ein = float((xin.real.double() ** 2 + xin.imag.double() ** 2).sum())
+        eout = float((yout.real.double() ** 2 + yout.imag.double() ** 2).sum()) / n
+        if not abs(eout - ein) <= 1e-5 * ein:
+            raise SystemExit(f"sanity check failed: Parseval {ein} vs {eout}")
+
+    # ---- end to end through the C ABI with pinned host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        del x, y
+        torch.cuda.empty_cache()
+        in_shape = (batch, n) if kind != "c2r" else (batch, n // 2 + 1)
+        out_shape = (batch, n) if kind != "r2c" else (batch, n // 2 + 1)
+        in_dtype = torch.float32 if kind == "r2c" else torch.complex64
+        out_dtype = torch.float32 if kind == "c2r" else torch.complex64
+        hx = torch.empty(in_shape, dtype=in_dtype, pin_memory=True)
+        hy = torch.empty(out_shape, dtype=out_dtype, pin_memory=True)
+        torch.view_as_real(hx).uniform_(-1, 1) if hx.is_complex() else hx.uniform_(-1, 1)
+        nx, ny = hx.numpy(), hy.numpy()
+        if kind == "c2c":
+            host_step = lambda: ctx.complex_forward(nx, ny)   # noqa: E731
+        elif kind == "r2c":
+            host_step = lambda: ctx.real_forward(nx, ny)      # noqa: E731
+        else:
+            host_step = lambda: ctx.real_inverse(nx, n, ny)   # noqa: E731
+        host_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            host_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        dt /= args.e2e_steps
+        e2e = {"value": round(spec["bytes"] * batch * world / dt / 1e9, 2), "unit": "GB/s",
+               "h2d_bytes_per_step": int(hx.numel() * hx.element_size()),
+               "d2h_bytes_per_step": int(hy.numel() * hy.element_size()),
+               "ms_per_step": round(dt * 1e3, 3), "steps": args.e2e_steps,
+               "gflops": round(spec["flops"] * batch * world / dt / 1e9, 1),
+               "path": "CkFft*Batch on pinned host arrays: 32 MiB chunks, 3 in flight, H2D/kernel/D2H overlapped; "
+                       "wall clock around the synchronous call, max over ranks"}
+        del hx, hy
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        per_gpu = gbs / world
+        line = {
+            "metric": METRIC, "value": round(gbs, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "gflops": round(gflops, 1), "gflops_convention": "5*N*log2(N) per complex transform (2.5*N*log2(N) real)",
+            "config": {"workload": spec["desc"], "n": n, "kind": kind, "batch_per_gpu": batch,
+                       "bytes_per_transform": spec["bytes"], "l2": "inputs larger than L2 (no flush needed)",
+                       "parallelism": f"batch-sharded x{world}, no collective"},
+            "roofline": {"bound": "hbm", "achieved": round(per_gpu, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(per_gpu / peak, 4), "traffic": ncu_traffic(spec["name"]),
+                         "peak_source": peak_src,
+                         "note": "achieved = 16*N bytes x transforms per launch / mean kernel time (one launch per step, "
+                                 "CUDA events on the launching stream), per GPU"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(spec)
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
