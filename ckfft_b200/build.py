@@ -32,6 +32,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-fvisibi
 UNITS = [
     ("api.o", "api.cu", []),
     ("tiny.o", "tiny.cu", []),
+    ("four_step.o", "four_step.cu", []),
     ("c2c_fwd.o", "fft_variants.cu", ["-DCKB_VARIANT=0"]),
     ("c2c_inv.o", "fft_variants.cu", ["-DCKB_VARIANT=1"]),
     ("r2c.o", "fft_variants.cu", ["-DCKB_VARIANT=2"]),

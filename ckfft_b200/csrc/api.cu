@@ -47,6 +47,11 @@ struct _CkFftContext
     int tableCount;          // Nt = min(maxCount, CKB_MAX_TABLE): entries in the device table
     int log2Table;
     float2* dTable;          // device: W_Nt^k = (cos, sin)(-2 pi k / Nt), forward sign
+    // multi-pass transforms (nMax > CKB_MAX_SINGLE_PASS): two-level twiddles of W_Tmax, Tmax = nMax
+    float2* dTwLo;           // W_Tmax^j,        j < 2^twH
+    float2* dTwHi;           // W_Tmax^(i<<twH), i < Tmax >> twH
+    int twH;
+    int log2Tmax;
 };
 
 namespace {
@@ -89,6 +94,70 @@ inline size_t out_elems(Kind k, int n) { return k == K_R2C ? (size_t) n / 2 + 1 
 inline size_t in_elem_bytes(Kind k)  { return k == K_R2C ? 4 : 8; }
 inline size_t out_elem_bytes(Kind k) { return k == K_C2R ? 4 : 8; }
 
+cudaError_t enqueue(const _CkFftContext* c, Kind kind, int n, const void* in, void* out, long long batch,
+                    long long in_stride, long long out_stride, cudaStream_t s);
+
+// ---- multi-pass lengths ---------------------------------------------------------------------
+// Scratch is stream-ordered (cudaMallocAsync / cudaFreeAsync): nothing mutable lives in the context.
+constexpr size_t kScratchCapBytes = size_t(2) << 30;
+
+ckb::BigTwiddles big_tw(const _CkFftContext* c) { return ckb::BigTwiddles{ c->dTwLo, c->dTwHi, c->twH, c->log2Tmax }; }
+
+cudaError_t enqueue_large_c2c(const _CkFftContext* c, bool inv, int n, const ckb::cf* in, ckb::cf* out, long long batch,
+                              long long in_stride, long long out_stride, cudaStream_t s)
+{
+    if (!c->dTwLo) return cudaErrorNotSupported;
+    if (in_stride != n || out_stride != n) return cudaErrorNotSupported;   // multi-pass path: dense batches only
+    const size_t per = (size_t) n * sizeof(ckb::cf);
+    long long sub = (long long) (kScratchCapBytes / per);
+    if (sub < 1) sub = 1;
+    if (sub > batch) sub = batch;
+    ckb::cf* scratch = nullptr;
+    cudaError_t e = cudaMallocAsync((void**) &scratch, per * (size_t) sub, s);
+    if (e != cudaSuccess) return e;
+    for (long long done = 0; done < batch && e == cudaSuccess; done += sub) {
+        const long long cnt = batch - done < sub ? batch - done : sub;
+        e = ckb::launch_four_step(inv, ilog2i(n), in + done * n, out + done * n, scratch, cnt, c->dTable, c->log2Table,
+                                  big_tw(c), s);
+    }
+    cudaError_t e2 = cudaFreeAsync(scratch, s);
+    return e != cudaSuccess ? e : e2;
+}
+
+// real n > CKB_MAX_TABLE: half-length complex transform (single- or multi-pass) + element-wise split / twist pass
+cudaError_t enqueue_large_real(const _CkFftContext* c, bool inverse, int n, const void* in, void* out, long long batch,
+                               long long in_stride, long long out_stride, cudaStream_t s)
+{
+    using ckb::cf;
+    if (!c->dTwLo) return cudaErrorNotSupported;
+    const int M = n / 2;
+    if ((!inverse && (in_stride != n || out_stride != M + 1)) || (inverse && (in_stride != M + 1 || out_stride != n)))
+        return cudaErrorNotSupported;
+    const size_t per = (size_t) M * sizeof(cf);
+    long long sub = (long long) (kScratchCapBytes / per);
+    if (sub < 1) sub = 1;
+    if (sub > batch) sub = batch;
+    cf* half = nullptr;      // Z (forward) or T (inverse): M complex per frame
+    cudaError_t e = cudaMallocAsync((void**) &half, per * (size_t) sub, s);
+    if (e != cudaSuccess) return e;
+    for (long long done = 0; done < batch && e == cudaSuccess; done += sub) {
+        const long long cnt = batch - done < sub ? batch - done : sub;
+        if (!inverse) {
+            const cf* x = (const cf*) ((const float*) in + done * n);      // n floats = M complex per frame
+            cf* y = (cf*) out + done * (M + 1);
+            e = enqueue(c, K_C2C_FWD, M, x, half, cnt, M, M, s);
+            if (e == cudaSuccess) e = ckb::launch_real_split(half, y, n, cnt, M, M + 1, big_tw(c), s);
+        } else {
+            const cf* y = (const cf*) in + done * (M + 1);
+            cf* x = (cf*) ((float*) out + done * n);
+            e = ckb::launch_real_twist(y, half, n, cnt, M + 1, M, big_tw(c), s);
+            if (e == cudaSuccess) e = enqueue(c, K_C2C_INV, M, half, x, cnt, M, M, s);
+        }
+    }
+    cudaError_t e2 = cudaFreeAsync(half, s);
+    return e != cudaSuccess ? e : e2;
+}
+
 // Enqueue `batch` transforms on DEVICE memory.  Strides are in elements of the respective array.
 // Returns cudaSuccess or the launch error.
 cudaError_t enqueue(const _CkFftContext* c, Kind kind, int n, const void* in, void* out, long long batch,
@@ -102,7 +171,7 @@ cudaError_t enqueue(const _CkFftContext* c, Kind kind, int n, const void* in, vo
         const bool inv = kind == K_C2C_INV;
         if (n <= 8) return launch_tiny_c2c(n, inv, p, s);
         if (n <= CKB_MAX_SINGLE_PASS) return inv ? launch_c2c_inv(n, p, s) : launch_c2c_fwd(n, p, s);
-        return cudaErrorNotSupported;
+        return enqueue_large_c2c(c, inv, n, (const cf*) in, (cf*) out, batch, in_stride, out_stride, s);
     }
     if (n <= 16) {
         return kind == K_R2C
@@ -119,7 +188,7 @@ cudaError_t enqueue(const _CkFftContext* c, Kind kind, int n, const void* in, vo
         KernelParams p{ (const cf*) in, (cf*) out, table, c->log2Table, batch, in_stride, out_stride / 2 };
         return launch_c2r(M, p, s);
     }
-    return cudaErrorNotSupported;
+    return enqueue_large_real(c, kind == K_C2R, n, in, out, batch, in_stride, out_stride, s);
 }
 
 // the reference's checks for one transform call (src/ckfft/ckfft.cpp:36-114), plus count <= 0
@@ -241,8 +310,8 @@ int run_host(const _CkFftContext* c, Kind kind, int n, const void* in, void* out
 
 bool supported_size(const _CkFftContext* c, Kind kind, int n)
 {
-    if (kind == K_C2C_FWD || kind == K_C2C_INV) return n <= CKB_MAX_SINGLE_PASS;
-    return n <= 16 || (n / 2 <= CKB_MAX_SINGLE_PASS && n <= c->tableCount);
+    (void) c; (void) kind;
+    return n <= (1 << 30);    // single pass up to 16384 complex / 32768 real points, multi-pass above
 }
 
 // shared body of the synchronous entry points
@@ -386,6 +455,39 @@ CkFftContext* CkFftInit(int maxCount, CkFftDirection direction, void* userBuf, s
         return NULL;
     }
 
+    // two-level inter-pass twiddles for multi-pass lengths, in double precision:
+    // W_Tmax^e = hi[e >> h] * lo[e & (2^h - 1)]
+    float2* dLo = NULL;
+    float2* dHi = NULL;
+    int twH = 0, log2Tmax = 0;
+    if (maxCount > CKB_MAX_SINGLE_PASS) {
+        log2Tmax = ilog2i(maxCount);
+        twH = (log2Tmax + 1) / 2;
+        const size_t nLo = size_t(1) << twH, nHi = size_t(1) << (log2Tmax - twH);
+        float2* host = (float2*) malloc((nLo + nHi) * sizeof(float2));
+        if (!host) e = cudaErrorMemoryAllocation;
+        else {
+            const double step = -2.0 * M_PI / (double) ((long long) 1 << log2Tmax);
+            for (size_t j = 0; j < nLo; ++j) { host[j].x = (float) cos(step * (double) j); host[j].y = (float) sin(step * (double) j); }
+            for (size_t i = 0; i < nHi; ++i) {
+                const double a = step * (double) (i << twH);
+                host[nLo + i].x = (float) cos(a);
+                host[nLo + i].y = (float) sin(a);
+            }
+            e = cudaMalloc((void**) &dLo, (nLo + nHi) * sizeof(float2));
+            if (e == cudaSuccess) e = cudaMemcpy(dLo, host, (nLo + nHi) * sizeof(float2), cudaMemcpyHostToDevice);
+            dHi = dLo ? dLo + nLo : NULL;
+            free(host);
+        }
+        if (e != cudaSuccess) {
+            set_error("device twiddle tables (multi-pass)", e);
+            if (dLo) cudaFree(dLo);
+            cudaFree(dTable);
+            if (!userBuf) free(buf);
+            return NULL;
+        }
+    }
+
     c->neon = false;
     c->maxCount = maxCount;
     c->fwdExpTable = fwd;
@@ -396,6 +498,10 @@ CkFftContext* CkFftInit(int maxCount, CkFftDirection direction, void* userBuf, s
     c->tableCount = nt;
     c->log2Table = ilog2i(nt);
     c->dTable = dTable;
+    c->dTwLo = dLo;
+    c->dTwHi = dHi;
+    c->twH = twH;
+    c->log2Tmax = log2Tmax;
     return c;
 }
 
@@ -406,6 +512,7 @@ void CkFftShutdown(CkFftContext* c)
     {
         DeviceGuard guard(c->device);
         if (c->dTable) cudaFree(c->dTable);
+        if (c->dTwLo) cudaFree(c->dTwLo);     // dTwHi lives in the same allocation
     }
     c->dTable = NULL;
     c->magic = 0;
@@ -493,6 +600,22 @@ int CkFftB200GetPlan(int n, int isReal, CkFftB200Plan* plan)
         plan->threadsPerTransform = 1;
         plan->elemsPerThread = m;
         plan->transformsPerCta = 128;
+        return 1;
+    }
+    if (m > CKB_MAX_SINGLE_PASS) {
+        if (n > (1 << 30)) return 0;
+        int npass = 0, L[3];
+        ckb::four_step_plan(ilog2i(m), &npass, L);
+        plan->passes = npass + (isReal ? 1 : 0);      // real: + one element-wise split / twist pass
+        for (int i = 0; i < npass && i < 2; ++i) {
+            const ckb::PlanRow* r = ckb::find_plan(L[i]);
+            plan->radix[i][0] = r->R0;
+            plan->radix[i][1] = r->R1;
+        }
+        const ckb::PlanRow* r0 = ckb::find_plan(L[0]);
+        plan->threadsPerTransform = r0->M / r0->E;    // threads per column of a tile
+        plan->elemsPerThread = r0->E;
+        plan->transformsPerCta = L[0] == 1024 ? 8 : 16;   // columns per tile
         return 1;
     }
     const ckb::PlanRow* r = ckb::find_plan(m);

@@ -1,0 +1,211 @@
+// four_step.cuh -- multi-pass ("four-step") transforms for lengths above the single-pass limit.
+//
+// A transform of N = L1*L2 (two passes, N <= 2^20) or N = L1*L2*L3 (three passes, N <= 2^30) points is
+// computed as passes of L-point FFTs (L = 128 .. 1024) over TILES of C adjacent columns:
+//
+//   column pass (KIND_COLUMN): problem of TN = L*ncols points viewed as [L][ncols]; the CTA stages the
+//       [L][C] tile through shared memory with row-chunk accesses (C*8 = 128 contiguous bytes per row,
+//       lanes run along the columns), transforms every column with the register/Stockham stages of
+//       fft_kernel.cuh, multiplies output (k, c) by the inter-pass twiddle W_TN^(c*k) -- fused into the
+//       store -- and writes the tile back in the same geometry;
+//   last pass (KIND_LAST): every column is a contiguous run of L points (lanes run along the transform),
+//       the result is scattered in natural order: output k of column c goes to c + ncols*k, again through
+//       a shared-memory tile so that each store is a 128-byte row chunk.
+//
+// Each pass is one HBM read + one HBM write of the whole array; intermediate results live in a
+// stream-ordered scratch buffer.  The reference has no equivalent (it recurses on one core,
+// src/ckfft/fft_default.cpp:168-266); the decomposition is the classic four-step / six-step algorithm
+// (cf. the vendored ext/fftw-3.3.2/mpi/dft-rank1.c:21-79 for the same index algebra).
+//
+// Inter-pass twiddles are W_Tmax^e with e up to 2^30: a full table is out of the question, so the context
+// carries a two-level table built in double precision, W^e = hi[e >> h] * lo[e & (2^h - 1)].
+#pragma once
+#include "fft_kernel.cuh"
+
+namespace ckb {
+
+enum TileKind { KIND_COLUMN = 0, KIND_LAST = 1 };
+
+struct TileParams {
+    const cf* in;
+    cf* out;
+    const cf* table;        // W_Nt^k for the stage LUT
+    int log2_nt;
+    const cf* tw_lo;        // two-level inter-pass twiddles, forward sign
+    const cf* tw_hi;
+    int tw_h;               // log2(entries of tw_lo)
+    int tw_shift;           // log2(Tmax) - log2(TN): scales an exponent of W_TN to one of W_Tmax
+    long long nproblems;    // independent problems of TN = L * ncols points, back to back
+    int ncols;              // columns per problem
+    int P, Q;               // KIND_LAST: input column c starts at ((c % P) * Q + c / P) * L
+};
+
+template <int L_, int E_, int R0_, int R1_, int C_, bool INV_, int KIND_, int MINB_>
+struct TileCfg {
+    static constexpr int L = L_, E = E_, R0 = R0_, R1 = R1_, C = C_, KIND = KIND_, MINB = MINB_;
+    static constexpr bool INV = INV_;
+    static constexpr int T = L / E;
+    static constexpr int THREADS = C * T;
+    static constexpr int LOGPAD = ilog2(R0);
+    static constexpr int XRAW = L + (L >> LOGPAD) + 1;
+    static constexpr int XBUF = XRAW | 1;                  // odd: the C columns of a row chunk hit distinct banks
+    static constexpr int LUT1 = (R1 - 1) * R0;
+    static constexpr int SMEM_BYTES = 8 * (LUT1 + C * XBUF);
+    static_assert(R0 * R1 == L && T <= 32 && THREADS <= 1024, "tile plan");
+    static_assert((L * C) % THREADS == 0 && (L * C) / THREADS == E, "one tile = E elements per thread");
+};
+
+__device__ __forceinline__ cf big_twiddle(const TileParams& p, unsigned c, unsigned k, bool inverse)
+{
+    const unsigned e = (c * k) << p.tw_shift;              // c*k < TN <= 2^30
+    const cf lo = __ldg(p.tw_lo + (e & ((1u << p.tw_h) - 1u)));
+    const cf hi = __ldg(p.tw_hi + (e >> p.tw_h));
+    cf w = cmul(lo, hi);
+    if (inverse) w.y = -w.y;
+    return w;
+}
+
+template <class TC>
+__global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileParams p)
+{
+    constexpr int L = TC::L, E = TC::E, T = TC::T, C = TC::C, R0 = TC::R0, R1 = TC::R1;
+    constexpr int LOGPAD = TC::LOGPAD, XBUF = TC::XBUF, THREADS = TC::THREADS;
+    constexpr bool INV = TC::INV;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf* lut1 = reinterpret_cast<cf*>(smem_raw);
+    cf* xall = lut1 + TC::LUT1;
+    const int tid = threadIdx.x;
+    const int g = tid / T;          // column of the tile owned by this thread's group
+    const int j = tid % T;
+    cf* xb = xall + g * XBUF;
+
+    {
+        const int sh1 = p.log2_nt - ilog2(L);
+        for (int i = tid; i < TC::LUT1; i += THREADS)
+            lut1[i] = table_w(p.table, ((i / R0 + 1) * (i % R0)) << sh1, INV);
+    }
+    __syncthreads();
+
+    const int blocks_per_problem = p.ncols / C;
+    const long long ntiles = p.nproblems * blocks_per_problem;
+    const long long tn = (long long) L * p.ncols;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long prob = tile / blocks_per_problem;
+        const int c0 = (int) (tile % blocks_per_problem) * C;
+        const cf* __restrict__ pin = p.in + prob * tn;
+        cf* __restrict__ pout = p.out + prob * tn;
+        cf v[E];
+
+        if constexpr (TC::KIND == KIND_COLUMN) {
+            // row-chunk gather of the [L][C] tile: consecutive lanes read consecutive columns
+            static_for<0, E>([&](auto i_) {
+                const int idx = tid + decltype(i_)::value * THREADS;
+                v[decltype(i_)::value] = ld_stream(pin + (long long) (idx / C) * p.ncols + c0 + (idx % C));
+            });
+            static_for<0, E>([&](auto i_) {
+                const int idx = tid + decltype(i_)::value * THREADS;
+                xall[(idx % C) * XBUF + padidx<LOGPAD>(idx / C)] = v[decltype(i_)::value];
+            });
+            __syncthreads();
+            stage_gather<L, T, E, R0, LOGPAD, SRC_XBUF>(v, nullptr, xb, j, true);
+            __syncwarp();
+        } else {
+            const int c = c0 + g;
+            const cf* src = pin + (long long) ((c % p.P) * p.Q + c / p.P) * L;
+            stage_gather<L, T, E, R0, LOGPAD, SRC_GLOBAL>(v, src, xb, j, true);
+        }
+        stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j);
+        stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xb, j, true);
+        __syncwarp();
+        stage_gather<L, T, E, R1, LOGPAD, SRC_XBUF>(v, nullptr, xb, j, true);
+        stage_math<T, E, R1, R0, INV, TW_LUT>(v, lut1, p.table, 0, j);
+        __syncwarp();
+        stage_scatter<L, T, E, R1, R0, LOGPAD, DST_XNAT>(v, nullptr, xb, j, true);
+        __syncthreads();
+
+        // row-chunk scatter of the transformed tile: output k of column c -> c + ncols * k
+#pragma unroll 4
+        for (int i = 0; i < E; ++i) {
+            const int idx = tid + i * THREADS;
+            const int c = idx % C, k = idx / C;
+            cf val = xall[c * XBUF + padidx<LOGPAD>(k)];
+            if constexpr (TC::KIND == KIND_COLUMN) val = cmul(val, big_twiddle(p, (unsigned) (c0 + c), (unsigned) k, INV));
+            st_stream(pout + (long long) k * p.ncols + c0 + c, val);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- real <-> half-length complex glue for n above the fused single-pass limit -------------------------
+// (the same split / twist as fft_real_default.cpp:13-114, as separate element-wise passes)
+struct RealGlueParams {
+    const cf* in;
+    cf* out;
+    const cf* tw_lo;
+    const cf* tw_hi;
+    int tw_h;
+    int tw_shift;          // log2(Tmax) - log2(n)
+    long long batch;
+    int M;                 // n / 2
+    long long in_stride, out_stride;   // complex elements per frame
+};
+
+__device__ __forceinline__ cf glue_twiddle(const RealGlueParams& p, unsigned k)
+{
+    const unsigned e = k << p.tw_shift;
+    return cmul(__ldg(p.tw_lo + (e & ((1u << p.tw_h) - 1u))), __ldg(p.tw_hi + (e >> p.tw_h)));
+}
+
+// Z[0..M) -> Y[0..M]   (forward split)
+__global__ void __launch_bounds__(256) real_split_kernel(const RealGlueParams p)
+{
+    const long long per = p.M / 2 + 1;
+    const long long total = p.batch * per;
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
+        const long long b = i / per;
+        const int k = (int) (i % per);
+        const cf* z = p.in + b * p.in_stride;
+        cf* y = p.out + b * p.out_stride;
+        if (k == p.M / 2) {
+            const cf m = z[k];
+            y[k] = make_float2(2.0f * m.x, -2.0f * m.y);
+            continue;
+        }
+        const cf z0 = z[k], z1 = z[(p.M - k) & (p.M - 1)];
+        const cf w = glue_twiddle(p, (unsigned) k);
+        const cf sum = make_float2(z0.x + z1.x, z0.y - z1.y);
+        const cf dif = make_float2(z0.x - z1.x, z0.y + z1.y);
+        const cf c = cmul(make_float2(-w.y, w.x), dif);
+        y[k] = make_float2(sum.x - c.x, sum.y - c.y);
+        y[p.M - k] = make_float2(sum.x + c.x, -(sum.y + c.y));
+    }
+}
+
+// Y[0..M] -> T[0..M)   (inverse twist)
+__global__ void __launch_bounds__(256) real_twist_kernel(const RealGlueParams p)
+{
+    const long long per = p.M / 2 + 1;
+    const long long total = p.batch * per;
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
+        const long long b = i / per;
+        const int k = (int) (i % per);
+        const cf* y = p.in + b * p.in_stride;
+        cf* t = p.out + b * p.out_stride;
+        if (k == p.M / 2) {
+            const cf m = y[k];
+            t[k] = make_float2(2.0f * m.x, -2.0f * m.y);
+            continue;
+        }
+        const cf y0 = y[k], y1 = y[p.M - k];
+        const cf w = glue_twiddle(p, (unsigned) k);
+        const cf sum = make_float2(y0.x + y1.x, y0.y - y1.y);
+        const cf dif = make_float2(y0.x - y1.x, y0.y + y1.y);
+        const cf c = cmul(make_float2(w.y, w.x), dif);
+        t[k] = make_float2(sum.x + c.x, sum.y + c.y);
+        if (k != 0) t[p.M - k] = make_float2(sum.x - c.x, -(sum.y - c.y));
+    }
+}
+
+}  // namespace ckb

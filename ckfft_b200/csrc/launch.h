@@ -21,6 +21,16 @@ cudaError_t launch_tiny_c2r(int n, const cf* in, float* out, const cf* table, in
 void count_launch();                  // api.cu: global launch counter
 int sm_count_of_current_device();     // api.cu: cached multiProcessorCount
 
+// multi-pass path (four_step.cu)
+struct BigTwiddles { const cf* lo; const cf* hi; int h; int log2_tmax; };   // W_Tmax^e = hi[e >> h] * lo[e & (2^h-1)]
+void four_step_plan(int log2n, int* npass, int L[3]);
+cudaError_t launch_four_step(bool inverse, int log2n, const cf* in, cf* out, cf* scratch, long long batch,
+                             const cf* table, int log2_nt, const BigTwiddles& tw, cudaStream_t s);
+cudaError_t launch_real_split(const cf* z, cf* y, int n, long long batch, long long z_stride, long long y_stride,
+                              const BigTwiddles& tw, cudaStream_t s);
+cudaError_t launch_real_twist(const cf* y, cf* t, int n, long long batch, long long y_stride, long long t_stride,
+                              const BigTwiddles& tw, cudaStream_t s);
+
 struct PlanRow { int M, E, R0, R1, R2, G, MINB, smem_bytes; };
 const PlanRow* find_plan(int M);      // launch.cu: nullptr if M is not a single-pass length
 

@@ -112,6 +112,17 @@ def test_planner_covers_every_power_of_two():
         assert p["shared_bytes"] <= 227 * 1024
         q = ck.get_plan(2 * n, real=True)
         assert q is not None and q["complex_points"] == n
+    for lg in range(15, 31):
+        p = ck.get_plan(1 << lg)
+        assert p is not None and p["passes"] == (2 if lg <= 20 else 3), (lg, p)
+        if lg <= 20:
+            prod = 1
+            for row in p["radix"]:
+                for r in row:
+                    prod *= r
+            assert prod == 1 << lg
+        q = ck.get_plan(1 << lg, real=True)
+        assert q is not None and q["complex_points"] == 1 << (lg - 1)
     assert ck.get_plan(24) is None and ck.get_plan(0) is None
     # the headline shapes: one warp per 1024-point transform, 32x32 radix split, 4 transforms per CTA
     p = ck.get_plan(1024)

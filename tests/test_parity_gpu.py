@@ -86,6 +86,67 @@ def test_real_vs_oracle(ctx_big, orc_big, n):
 
 
 # ---------------------------------------------------------------------------------------------
+# multi-pass lengths (four-step: two passes up to 2^20, three passes above)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("log2n", [15, 16, 17, 18, 19, 20, 21, 22, 24])
+def test_large_complex_vs_oracle(log2n):
+    n = 1 << log2n
+    batch = 3 if log2n <= 18 else 1
+    rng = np.random.default_rng(log2n)
+    x = uniform_complex(rng, (batch, n))
+    orc = oracle.Restatement(n, 3)
+    with ck.Context(n, ck.BOTH) as ctx:
+        for inverse in (False, True):
+            want = orc.complex(x, inverse)
+            f = ctx.complex_inverse if inverse else ctx.complex_forward
+            got = f(torch.from_numpy(x).cuda()).cpu().numpy()
+            assert rel_rms(got, want) <= tolerance(n), (n, inverse)
+            assert rel_rms(got, oracle.fp64_c2c(x, inverse)) <= tolerance(n)
+        if log2n <= 18:
+            assert np.array_equal(ctx.complex_forward(x).view(np.uint32),
+                                  ctx.complex_forward(torch.from_numpy(x).cuda()).cpu().numpy().view(np.uint32))
+    orc.close()
+
+
+@pytest.mark.parametrize("log2n", [16, 17, 20, 22])
+def test_large_real_vs_oracle(log2n):
+    n = 1 << log2n
+    batch = 2 if log2n <= 17 else 1
+    rng = np.random.default_rng(50 + log2n)
+    x = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    orc = oracle.Restatement(n, 3)
+    with ck.Context(n, ck.BOTH) as ctx:
+        want = orc.real_forward(x)
+        got = ctx.real_forward(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert rel_rms(got, want) <= tolerance(n)
+        assert rel_rms(got, oracle.fp64_real_forward(x)) <= tolerance(n)
+        back = ctx.real_inverse(torch.from_numpy(want).cuda(), n).cpu().numpy()
+        assert rel_rms(back, orc.real_inverse(want, n)) <= tolerance(n)
+        assert rel_rms(back, 2.0 * n * x.astype(np.float64)) <= tolerance(n)
+    orc.close()
+
+
+def test_very_large_round_trip_2_26():
+    """N = 2^26 (three passes, 512 MiB per array): inverse(forward(x)) = N x, Parseval, and two analytic bins."""
+    n = 1 << 26
+    g = torch.Generator(device="cuda").manual_seed(99)
+    x = torch.view_as_complex(torch.empty((1, n, 2), dtype=torch.float32, device="cuda").uniform_(-1, 1, generator=g))
+    with ck.Context(n, ck.BOTH) as ctx:
+        y = ctx.complex_forward(x)
+        e_in = float((x.real.double() ** 2 + x.imag.double() ** 2).sum())
+        e_out = float((y.real.double() ** 2 + y.imag.double() ** 2).sum()) / n
+        assert abs(e_out - e_in) <= 1e-5 * e_in
+        dc = complex(x.real.double().sum().item(), x.imag.double().sum().item())
+        assert abs(complex(y[0, 0].item()) - dc) <= 1e-3 * np.sqrt(n)
+        sign = torch.ones(n, dtype=torch.float64, device="cuda"); sign[1::2] = -1
+        nyq = complex((x.real.double()[0] * sign).sum().item(), (x.imag.double()[0] * sign).sum().item())
+        assert abs(complex(y[0, n // 2].item()) - nyq) <= 1e-3 * np.sqrt(n)
+        z = ctx.complex_inverse(y)
+        err = float(torch.linalg.vector_norm((z / n - x).abs().double()) / torch.linalg.vector_norm(x.abs().double()))
+        assert err <= tolerance(n)
+
+
+# ---------------------------------------------------------------------------------------------
 # the reference's own fixture and acceptance criteria (golden vectors generated from the reference)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [1 << k for k in range(0, 13)])
