@@ -59,9 +59,76 @@ __device__ __forceinline__ void group_sync(int g)
     }
 }
 
-enum Src { SRC_GLOBAL = 0, SRC_XBUF = 1 };
+// ---- bulk asynchronous copies (cp.async.bulk = TMA's 1-D mode, SASS UBLKCP) and their mbarriers ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    while (!mbar_try_wait(bar, parity)) { }
+}
+
+__device__ __forceinline__ unsigned long long l2_evict_first_policy()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is signalled on `bar`
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+enum Src { SRC_GLOBAL = 0, SRC_XBUF = 1, SRC_INBUF = 2 };
 enum Dst { DST_GLOBAL = 0, DST_XCHG = 1, DST_XNAT = 2 };
-enum Tw { TW_NONE = 0, TW_LUT = 1, TW_TABLE = 2 };
+enum Tw { TW_NONE = 0, TW_LUT = 1, TW_TABLE = 2, TW_REGS = 3 };
+
+// TW_REGS: the stage twiddles W^(t*m), t = a*LO + b, are rebuilt from LO-1 + HI-1 table values that the
+// thread keeps in registers for the whole kernel:  W^(t*m) = W^(a*LO*m) * W^(b*m)  (one extra rounding on
+// the products, none on the bases).  Removes the per-transform LUT traffic from the shared-memory port.
+template <int R> struct TwSplit {
+    static constexpr int LO = R >= 32 ? 8 : (R >= 8 ? 4 : 2);
+    static constexpr int HI = R / LO;
+    static constexpr int NB = (LO - 1) + (HI - 1);
+};
+
+template <int R, bool INV>
+__device__ __forceinline__ void load_tw_bases(cf (&twb)[TwSplit<R>::NB], const cf* __restrict__ table, int m, int tshift)
+{
+    constexpr int LO = TwSplit<R>::LO, HI = TwSplit<R>::HI;
+    static_for<1, LO>([&](auto b_) { constexpr int b = decltype(b_)::value; twb[b - 1] = table_w(table, (m * b) << tshift, INV); });
+    static_for<1, HI>([&](auto a_) { constexpr int a = decltype(a_)::value; twb[LO - 1 + a - 1] = table_w(table, (m * LO * a) << tshift, INV); });
+}
+
+template <int R, int TT>
+__device__ __forceinline__ cf tw_from_bases(const cf (&twb)[TwSplit<R>::NB])
+{
+    constexpr int LO = TwSplit<R>::LO;
+    constexpr int a = TT / LO, b = TT % LO;
+    if constexpr (a == 0) return twb[b - 1];
+    else if constexpr (b == 0) return twb[LO - 1 + a - 1];
+    else return cmul(twb[LO - 1 + a - 1], twb[b - 1]);
+}
 
 // One Stockham stage = gather + math + scatter over the E register values of a thread.  They are
 // separate so the kernel can put a group barrier between a shared-memory gather and the scatter
@@ -79,12 +146,67 @@ __device__ __forceinline__ void stage_gather(cf (&v)[E], const cf* __restrict__ 
             constexpr int t = decltype(t_)::value;
             constexpr int slot = q * R + bitrev<R>(t);
             if constexpr (SRC == SRC_GLOBAL) {
-                v[slot] = valid ? ld_stream(gsrc + jq + t * STR) : make_float2(0.f, 0.f);
+                if (valid) v[slot] = ld_stream(gsrc + jq + t * STR);   // an invalid group computes on garbage and stores nothing
+            } else if constexpr (SRC == SRC_INBUF) {
+                v[slot] = xb[jq + t * STR];            // dense staging buffer filled by a bulk copy
             } else {
                 v[slot] = xb[padidx<LOGPAD>(jq + t * STR)];
             }
         });
     });
+}
+
+// Last stage of the three-stage plans: per butterfly q the thread keeps W^(m*2^i), i < log2(R), in registers
+// (exact table values; m = j + q*T is loop invariant) and forms W^(m*t) as W^(m*(t - msb)) * W^(m*msb):
+// one complex multiply per non-power-of-two t, at most log2(R)-1 roundings deep.
+template <int T, int E, int R, bool INV>
+__device__ __forceinline__ void load_pow_bases(cf (&pw)[(E / R) * ilog2(R)], const cf* __restrict__ table, int j, int tshift)
+{
+    constexpr int B = E / R, LG = ilog2(R);
+    static_for<0, B>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        const int m = j + q * T;
+        static_for<0, LG>([&](auto i_) {
+            constexpr int i = decltype(i_)::value;
+            pw[q * LG + i] = table_w(table, (m << i) << tshift, INV);
+        });
+    });
+}
+
+template <int R, int TT, int LG, int NPW>
+__device__ __forceinline__ cf pow_twiddle(const cf (&pw)[NPW], int qoff)
+{
+    constexpr int msb = 1 << (ilog2(TT + 1) - 1);       // highest set bit of TT
+    if constexpr (TT == msb) return pw[qoff + ilog2(msb)];
+    else return cmul(pow_twiddle<R, TT - msb, LG, NPW>(pw, qoff), pw[qoff + ilog2(msb)]);
+}
+
+template <int E, int R, bool INV>
+__device__ __forceinline__ void stage_math_pow(cf (&v)[E], const cf (&pw)[(E / R) * ilog2(R)])
+{
+    constexpr int B = E / R, LG = ilog2(R);
+    static_for<0, B>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        static_for<1, R>([&](auto t_) {
+            constexpr int t = decltype(t_)::value;
+            constexpr int slot = q * R + bitrev<R>(t);
+            v[slot] = cmul(v[slot], pow_twiddle<R, t, LG, B * LG>(pw, q * LG));
+        });
+    });
+    static_for<0, B>([&](auto q_) { fft_regs<R, decltype(q_)::value * R, INV>(v); });
+}
+
+// stage_math with register-resident twiddle bases (one butterfly per thread: m is loop invariant)
+template <int E, int R, bool INV>
+__device__ __forceinline__ void stage_math_regs(cf (&v)[E], const cf (&twb)[TwSplit<R>::NB])
+{
+    static_assert(E == R, "TW_REGS needs one butterfly per thread");
+    static_for<1, R>([&](auto t_) {
+        constexpr int t = decltype(t_)::value;
+        constexpr int slot = bitrev<R>(t);
+        v[slot] = cmul(v[slot], tw_from_bases<R, t>(twb));
+    });
+    fft_regs<R, 0, INV>(v);
 }
 
 template <int T, int E, int R, int NS, bool INV, int TW>
@@ -133,8 +255,19 @@ __device__ __forceinline__ void stage_scatter(const cf (&v)[E], cf* __restrict__
 }
 
 // Compile-time description of one kernel variant.
-template <int M_, int E_, int R0_, int R1_, int R2_, int G_, bool INV_, int MODE_, int MINB_ = 1>
+// PF_ = true: every group owns a dense staging buffer that a bulk asynchronous copy (cp.async.bulk)
+// refills with its NEXT transform while the current one is being computed: the load of item i+1 is in
+// flight from the end of item i's first gather until item i+1 starts.
+//
+// PF_ = 2: same idea without the second buffer: the bulk copy of the next transform lands in the exchange
+// buffer itself as soon as the last gather of the current transform has drained it, so it overlaps the
+// last stage's arithmetic and the stores (no extra shared memory, occupancy unchanged).
+enum Prefetch { PF_NONE = 0, PF_DOUBLE = 1, PF_INPLACE = 2 };
+
+template <int M_, int E_, int R0_, int R1_, int R2_, int G_, bool INV_, int MODE_, int MINB_ = 1, int PF_ = PF_NONE, bool TWR_ = false>
 struct Cfg {
+    static constexpr int PF = PF_;
+    static constexpr bool TWR = TWR_;       // stage-1 twiddles from register-resident bases (two-stage plans with R1 == E)
     static constexpr int M = M_, E = E_, R0 = R0_, R1 = R1_, R2 = R2_, G = G_, MODE = MODE_, MINB = MINB_;
     static constexpr bool INV = INV_;
     static constexpr int T = M / E;
@@ -142,10 +275,16 @@ struct Cfg {
     static constexpr int NSTAGE = R2 > 1 ? 3 : 2;
     static constexpr int LOGPAD = ilog2(R0);
     static constexpr int XBUF = M + (M >> LOGPAD) + 2;          // complex slots per group (+ slot M for the real modes)
-    static constexpr int LUT1 = (R1 - 1) * R0;                  // stage 1: Ns = R0
+    static constexpr int LUT1 = TWR_ ? 0 : (R1 - 1) * R0;       // stage 1: Ns = R0
     static constexpr bool LUT2_SMEM = NSTAGE == 3 && (R2 - 1) * R0 * R1 <= 4096;
+    static constexpr bool POW2 = NSTAGE == 3 && !LUT2_SMEM;        // last-stage twiddles from register power bases
+    static constexpr int NPOW = POW2 ? (E / R2) * ilog2(R2) : 1;
     static constexpr int LUT2 = LUT2_SMEM ? (R2 - 1) * R0 * R1 : 0;   // stage 2: Ns = R0*R1
-    static constexpr int SMEM_BYTES = 8 * (LUT1 + LUT2 + G * XBUF);
+    static constexpr int GROUP_SLOTS = XBUF + (PF == PF_DOUBLE ? M : 0);     // exchange buffer (+ staging buffer)
+    static constexpr int SMEM_BYTES = 8 * (LUT1 + LUT2 + G * GROUP_SLOTS) + (PF ? 8 * G : 0);
+    static_assert(!PF || MODE_ != MODE_C2R, "the half-spectrum rows of C2R are not 16-byte aligned");
+    static_assert(PF != PF_INPLACE || MODE_ == MODE_C2C, "in-place prefetch: the real epilogue still owns the buffer");
+    static_assert(!TWR_ || R1_ == E_, "TWR: stage 1 must be one butterfly per thread (m = j mod R0 is loop invariant)");
     static_assert(R0 * R1 * R2 == M, "radices must multiply to the transform length");
     static_assert(R0 <= E && R1 <= E && R2 <= E, "a butterfly must fit one thread");
     static_assert(T <= 32 || G <= 15, "named barriers 1..15");
@@ -165,7 +304,15 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
     const int tid = threadIdx.x;
     const int g = tid / T;
     const int j = tid % T;
-    cf* xb = lut2 + C::LUT2 + g * C::XBUF;
+    cf* xb = lut2 + C::LUT2 + g * C::GROUP_SLOTS;
+    cf* inb = C::PF == PF_DOUBLE ? xb + C::XBUF : xb;                  // staging buffer of the bulk copies
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(lut2 + C::LUT2 + G * C::GROUP_SLOTS) + g;
+    unsigned long long l2pol = 0;
+    if constexpr (C::PF) {
+        if (j == 0) mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        l2pol = l2_evict_first_policy();
+    }
 
     // stage twiddle LUTs, [t-1][m] so that a thread's R-1 loads are immediate offsets from one base
     {
@@ -183,6 +330,31 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
 
     const int sh_last = p.log2_nt - ilog2(M);        // W_M^k   = table[k << sh_last]
     const int sh_real = p.log2_nt - ilog2(2 * M);    // W_2M^k  = table[k << sh_real]  (real modes)
+
+    cf twb[TwSplit<R1>::NB];
+    if constexpr (C::TWR) load_tw_bases<R1, INV>(twb, p.table, j & (R0 - 1), p.log2_nt - ilog2(R0 * R1));
+    cf pw[C::NPOW];
+    if constexpr (C::POW2) load_pow_bases<T, E, R2, INV>(pw, p.table, j, p.log2_nt - ilog2(M));
+
+    unsigned phase = 0;
+    if constexpr (C::PF) {
+        const long long first = (long long) blockIdx.x * G + g;
+        if (j == 0 && first < p.batch) {
+            mbar_expect_tx(mbar, M * 8);
+            bulk_load(inb, p.in + first * p.in_stride, M * 8, mbar, l2pol);
+        }
+    }
+
+    // one thread per group refills the staging buffer with the group's next transform
+    auto issue_next = [&](long long item) {
+        const long long next = item + (long long) gridDim.x * G;
+        if (j == 0 && next < p.batch) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(mbar, M * 8);
+            bulk_load(inb, p.in + next * p.in_stride, M * 8, mbar, l2pol);
+        }
+    };
+    (void) issue_next;
 
     for (long long base = (long long) blockIdx.x * G; base < p.batch; base += (long long) gridDim.x * G) {
         const long long item = base + g;
@@ -213,6 +385,12 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             group_sync<T>(g);
             stage_gather<M, T, E, R0, LOGPAD, SRC_XBUF>(v, src, xb, j, valid);
             group_sync<T>(g);
+        } else if constexpr (C::PF != PF_NONE) {
+            if (valid) mbar_wait(mbar, phase);
+            phase ^= 1u;
+            stage_gather<M, T, E, R0, LOGPAD, SRC_INBUF>(v, src, inb, j, valid);
+            group_sync<T>(g);                      // every thread of the group has drained the staging buffer
+            if constexpr (C::PF == PF_DOUBLE) issue_next(item);
         } else {
             stage_gather<M, T, E, R0, LOGPAD, SRC_GLOBAL>(v, src, xb, j, valid);
         }
@@ -222,7 +400,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
 
         // ---- stage 1 (Ns = R0) ----
         stage_gather<M, T, E, R1, LOGPAD, SRC_XBUF>(v, src, xb, j, valid);
-        stage_math<T, E, R1, R0, INV, TW_LUT>(v, lut1, p.table, 0, j);
+        if constexpr (C::PF == PF_INPLACE && C::NSTAGE == 2) { group_sync<T>(g); issue_next(item); }
+        if constexpr (C::TWR) stage_math_regs<E, R1, INV>(v, twb);
+        else                  stage_math<T, E, R1, R0, INV, TW_LUT>(v, lut1, p.table, 0, j);
         if constexpr (C::NSTAGE == 2) {
             if constexpr (MODE == MODE_R2C) {
                 group_sync<T>(g);
@@ -235,9 +415,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XCHG>(v, dst, xb, j, valid);
             group_sync<T>(g);
             // ---- stage 2 (Ns = R0*R1) ----
-            constexpr int TW2 = C::LUT2_SMEM ? TW_LUT : TW_TABLE;
             stage_gather<M, T, E, R2, LOGPAD, SRC_XBUF>(v, src, xb, j, valid);
-            stage_math<T, E, R2, R0 * R1, INV, TW2>(v, lut2, p.table, sh_last, j);
+            if constexpr (C::PF == PF_INPLACE) { group_sync<T>(g); issue_next(item); }
+            if constexpr (C::POW2) stage_math_pow<E, R2, INV>(v, pw);
+            else                   stage_math<T, E, R2, R0 * R1, INV, TW_LUT>(v, lut2, p.table, sh_last, j);
             if constexpr (MODE == MODE_R2C) {
                 group_sync<T>(g);
                 stage_scatter<M, T, E, R2, R0 * R1, LOGPAD, DST_XNAT>(v, dst, xb, j, valid);
@@ -269,7 +450,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             }
         }
         // the next iteration's first scatter must not overtake this iteration's last gather
-        group_sync<T>(g);
+        // (the in-place prefetch already put a group barrier behind that gather)
+        if constexpr (C::PF != PF_INPLACE) group_sync<T>(g);
     }
 }
 

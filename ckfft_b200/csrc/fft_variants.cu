@@ -6,6 +6,8 @@
 //   3  real inverse      (CkFftRealInverse,     :55-76)   fused twist + half-length inverse FFT
 #include "launch.h"
 #include "plans.h"
+#include <stdint.h>
+#include <stdlib.h>
 
 #ifndef CKB_VARIANT
 #error "compile with -DCKB_VARIANT=0..3"
@@ -26,6 +28,17 @@ static constexpr bool kInv = false; static constexpr int kMode = MODE_R2C;
 #define CKB_FN launch_c2r
 static constexpr bool kInv = true; static constexpr int kMode = MODE_C2R;
 #endif
+
+static int prefetch_mode()
+{
+    // CKFFT_B200_PREFETCH=0 disables the bulk-prefetch kernels (development switch, read once)
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("CKFFT_B200_PREFETCH");
+        mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    return mode;
+}
 
 template <class C>
 static cudaError_t launch_cfg(const KernelParams& p, cudaStream_t s)
@@ -56,9 +69,32 @@ static cudaError_t launch_cfg(const KernelParams& p, cudaStream_t s)
 
 cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
 {
+#if CKB_VARIANT != 3
+    // bulk copies need 16-byte aligned rows
+    if (prefetch_mode() && ((uintptr_t) p.in & 15) == 0 && (p.in_stride & 1) == 0) {
+        switch (M) {
+#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_DOUBLE, TWR_ != 0>>(p, s);
+            CKB_PREFETCH_PLANS(X)
+#undef X
+            default: break;
+        }
+    }
+#endif
+#if CKB_VARIANT <= 1
+    if (prefetch_mode() && ((uintptr_t) p.in & 15) == 0 && (p.in_stride & 1) == 0) {
+        switch (M) {
+#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0>>(p, s);
+            CKB_INPLACE_PREFETCH_PLANS(X)
+#undef X
+            default: break;
+        }
+    }
+#endif
     switch (M) {
-#define X(M_, E_, R0_, R1_, R2_, G_, MINB_) \
-    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_>>(p, s);
+#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0>>(p, s);
         CKB_SINGLE_PASS_PLANS(X)
 #undef X
         default: return cudaErrorInvalidValue;

@@ -1,25 +1,41 @@
 // plans.h -- the single-pass plan table: one row per complex transform length M.
-//   X(M, E, R0, R1, R2, G, MINB)
+//   X(M, E, R0, R1, R2, G, MINB, TWR)
 //     E    complex values per thread (registers)      T = M/E threads per transform
 //     R*   radices of the 2 or 3 Stockham stages (R2 = 1: two stages)
 //     G    transforms per CTA                         CTA = G*T threads
 //     MINB __launch_bounds__ min CTAs/SM (caps registers so that many CTAs stay resident)
+//     TWR  1: stage-1 twiddles live in registers for the whole kernel (two-stage plans with R1 == E)
 // The launch planner (launch.cu) and CkFftB200GetPlan (api.cu) both expand this table, so the
 // host-visible plan is by construction the kernel that runs.
 #pragma once
 
 #define CKB_SINGLE_PASS_PLANS(X) \
-    X(16,     4,  4,  4,  1, 32, 8) \
-    X(32,     8,  8,  4,  1, 32, 8) \
-    X(64,     8,  8,  8,  1, 16, 8) \
-    X(128,   16, 16,  8,  1, 16, 4) \
-    X(256,   16, 16, 16,  1,  8, 4) \
-    X(512,   32, 32, 16,  1,  8, 4) \
-    X(1024,  32, 32, 32,  1,  4, 4) \
-    X(2048,  32, 32, 32,  2,  4, 2) \
-    X(4096,  16, 16, 16, 16,  2, 2) \
-    X(8192,  32, 32, 16, 16,  1, 2) \
-    X(16384, 32, 32, 32, 16,  1, 1)
+    X(16,     4,  4,  4,  1, 32, 8, 1) \
+    X(32,     8,  8,  4,  1, 32, 8, 0) \
+    X(64,     8,  8,  8,  1, 16, 8, 1) \
+    X(128,   16, 16,  8,  1, 16, 4, 0) \
+    X(256,   16, 16, 16,  1,  8, 4, 1) \
+    X(512,   32, 32, 16,  1,  8, 4, 0) \
+    X(1024,  32, 32, 32,  1,  4, 4, 1) \
+    X(2048,  32, 32, 32,  2,  4, 2, 0) \
+    X(4096,  32, 32, 32,  4,  2, 2, 0) \
+    X(8192,  32, 32, 32,  8,  1, 2, 0) \
+    X(16384, 32, 32, 32, 16,  1, 1, 0)
 
+// Bulk-prefetch variants (Cfg::PF): each group's next transform is fetched by cp.async.bulk into a dense
+// staging buffer while the current one is computed.  Used for complex and real-forward transforms whose
+// rows are 16-byte aligned (CKFFT_B200_PREFETCH=0 disables them, for A/B measurements).
+#define CKB_PREFETCH_PLANS(X) \
+    X(1024,  32, 32, 32,  1,  4, 3, 1)
+
+// In-place prefetch variants (Cfg::PF == PF_INPLACE), complex transforms only.  Measured on B200 (fraction of
+// the 6.55 TB/s copy peak, without -> with): 256 .89->.94, 512 .87->.95, 2048 .90->.95, 4096 .66->.95,
+// 8192 .74->.87; rows shorter than 2 KiB lose (too many tiny bulk copies), 16384 loses (.64->.59).
+#define CKB_INPLACE_PREFETCH_PLANS(X) \
+    X(256,   16, 16, 16,  1,  8, 4, 1) \
+    X(512,   32, 32, 16,  1,  8, 4, 0) \
+    X(2048,  32, 32, 32,  2,  4, 2, 0) \
+    X(4096,  32, 32, 32,  4,  2, 2, 0) \
+    X(8192,  32, 32, 32,  8,  1, 2, 1)
 #define CKB_MAX_SINGLE_PASS 16384   /* largest complex length done in one launch */
 #define CKB_MAX_TABLE 32768         /* device twiddle table W_Nt^k covers real n up to this in one pass */

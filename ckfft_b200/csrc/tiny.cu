@@ -65,8 +65,8 @@ cudaError_t launch_tiny_c2r(int n, const cf* in, float* out, const cf* table, in
 }
 
 static const PlanRow kPlans[] = {
-#define X(M_, E_, R0_, R1_, R2_, G_, MINB_) \
-    { M_, E_, R0_, R1_, R2_, G_, MINB_, Cfg<M_, E_, R0_, R1_, R2_, G_, false, MODE_C2C, MINB_>::SMEM_BYTES },
+#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
+    { M_, E_, R0_, R1_, R2_, G_, MINB_, Cfg<M_, E_, R0_, R1_, R2_, G_, false, MODE_C2C, MINB_, PF_NONE, TWR_ != 0>::SMEM_BYTES },
     CKB_SINGLE_PASS_PLANS(X)
 #undef X
 };

@@ -21,7 +21,7 @@ def rel(a, b):
 def parity():
     rng = np.random.default_rng(7)
     worst = 0.0
-    for lg in range(0, 16):
+    for lg in (range(0, 16) if len(sys.argv) <= 1 else []):
         n = 1 << lg
         nb = 37 if n <= 4096 else 5
         ctx = ck.Context(max(n, 2), ck.BOTH)
@@ -67,8 +67,6 @@ def sweep(sizes, total_log2=27, iters=10):
         out = torch.empty_like(x)
         for kind in ("c2c", "r2c", "c2r"):
             if kind == "c2c":
-                if n > 16384:
-                    continue
                 f = lambda: ctx.complex_forward(x, out)
                 nbytes = 16 * n * batch
                 flops = 5 * n * np.log2(n) * batch
@@ -103,5 +101,8 @@ if __name__ == "__main__":
     t = time.time()
     w = parity()
     print(f"parity took {time.time() - t:.1f}s")
-    sweep([1 << k for k in range(4, 16)])
+    sizes = [1 << k for k in range(4, 23)]
+    if len(sys.argv) > 1:
+        sizes = [int(a) for a in sys.argv[1:]]
+    sweep(sizes)
     sys.exit(0 if w < 1e-6 else 1)
