@@ -130,10 +130,27 @@ __device__ __forceinline__ cf tw_from_bases(const cf (&twb)[TwSplit<R>::NB])
     else return cmul(twb[LO - 1 + a - 1], twb[b - 1]);
 }
 
+// Which butterfly (0 .. M/R-1) register block q of thread j works on.  The usual map is j + q*T.  The
+// PAIRED map (last stage of the real-forward kernel) hands a thread butterflies in mirror pairs
+// (p, STR - p): butterfly p yields Z[p + u*STR] and its mirror images Z[M - (p + u*STR)] =
+// Z[(STR - p) + (R-1-u)*STR] all come from butterfly STR - p, so the real split
+// (fft_real_default.cpp:30-58) runs entirely in this thread's registers.  Butterflies 0 and STR/2 are their
+// own mirrors and share the pair slot of thread 0.
+template <int T, int STR, bool PAIRED>
+__device__ __forceinline__ int bfly_index(int j, int q)
+{
+    if constexpr (!PAIRED) return j + q * T;
+    else {
+        const int p = j + (q >> 1) * T;
+        if ((q & 1) == 0) return p;
+        return p == 0 ? STR / 2 : STR - p;
+    }
+}
+
 // One Stockham stage = gather + math + scatter over the E register values of a thread.  They are
 // separate so the kernel can put a group barrier between a shared-memory gather and the scatter
 // that reuses the same buffer.
-template <int M, int T, int E, int R, int LOGPAD, int SRC>
+template <int M, int T, int E, int R, int LOGPAD, int SRC, bool PAIRED = false>
 __device__ __forceinline__ void stage_gather(cf (&v)[E], const cf* __restrict__ gsrc, const cf* xb, int j, bool valid)
 {
     constexpr int B = E / R;      // butterflies per thread
@@ -141,7 +158,7 @@ __device__ __forceinline__ void stage_gather(cf (&v)[E], const cf* __restrict__ 
     static_assert(B * R == E, "radix must divide the per-thread element count");
     static_for<0, B>([&](auto q_) {
         constexpr int q = decltype(q_)::value;
-        const int jq = j + q * T;
+        const int jq = bfly_index<T, STR, PAIRED>(j, q);
         static_for<0, R>([&](auto t_) {
             constexpr int t = decltype(t_)::value;
             constexpr int slot = q * R + bitrev<R>(t);
@@ -159,13 +176,13 @@ __device__ __forceinline__ void stage_gather(cf (&v)[E], const cf* __restrict__ 
 // Last stage of the three-stage plans: per butterfly q the thread keeps W^(m*2^i), i < log2(R), in registers
 // (exact table values; m = j + q*T is loop invariant) and forms W^(m*t) as W^(m*(t - msb)) * W^(m*msb):
 // one complex multiply per non-power-of-two t, at most log2(R)-1 roundings deep.
-template <int T, int E, int R, bool INV>
+template <int M, int T, int E, int R, bool INV, bool PAIRED>
 __device__ __forceinline__ void load_pow_bases(cf (&pw)[(E / R) * ilog2(R)], const cf* __restrict__ table, int j, int tshift)
 {
     constexpr int B = E / R, LG = ilog2(R);
     static_for<0, B>([&](auto q_) {
         constexpr int q = decltype(q_)::value;
-        const int m = j + q * T;
+        const int m = bfly_index<T, M / R, PAIRED>(j, q);
         static_for<0, LG>([&](auto i_) {
             constexpr int i = decltype(i_)::value;
             pw[q * LG + i] = table_w(table, (m << i) << tshift, INV);
@@ -209,14 +226,15 @@ __device__ __forceinline__ void stage_math_regs(cf (&v)[E], const cf (&twb)[TwSp
     fft_regs<R, 0, INV>(v);
 }
 
-template <int T, int E, int R, int NS, bool INV, int TW>
+template <int T, int E, int R, int NS, bool INV, int TW, bool PAIRED = false>
 __device__ __forceinline__ void stage_math(cf (&v)[E], const cf* lut, const cf* __restrict__ table, int tshift, int j)
 {
     constexpr int B = E / R;
+    static_assert(!PAIRED || NS * R == T * E, "the paired map is for the last stage (STR == NS)");
     if constexpr (TW != TW_NONE) {
         static_for<0, B>([&](auto q_) {
             constexpr int q = decltype(q_)::value;
-            const int m = (j + q * T) & (NS - 1);
+            const int m = bfly_index<T, NS, PAIRED>(j, q) & (NS - 1);
             static_for<1, R>([&](auto t_) {
                 constexpr int t = decltype(t_)::value;
                 constexpr int slot = q * R + bitrev<R>(t);
@@ -254,6 +272,57 @@ __device__ __forceinline__ void stage_scatter(const cf (&v)[E], cf* __restrict__
     });
 }
 
+// Real-forward split on a thread's mirror-paired butterflies (see bfly_index).  v holds, per pair slot s,
+// Z[p + u*STR] in block 2s and Z[pbar + u*STR] in block 2s+1 (natural u order).  Writes Y[0 .. M].
+//   Y[k] = (Z[k] + conj Z[M-k]) - i W_2M^k (Z[k] - conj Z[M-k]);  with c = i W^k * diff:
+//   Y[k] = sum - c,  Y[M-k] = conj(sum + c)          (the two statements of fft_real_default.cpp:30-58)
+template <int M, int T, int E, int R>
+__device__ __forceinline__ void r2c_paired_epilogue(const cf (&v)[E], cf* __restrict__ dst, const cf* __restrict__ table,
+                                                    int sh_real, int j, bool valid)
+{
+    constexpr int B = E / R, STR = M / R;
+    static_assert(B % 2 == 0, "butterflies come in mirror pairs");
+    auto emit = [&](cf z0, cf z1, int k) {
+        const cf w = __ldg(table + (k << sh_real));        // W_2M^k; f = i w = (-w.y, w.x)
+        const cf sum = make_float2(z0.x + z1.x, z0.y - z1.y);
+        const cf dif = make_float2(z0.x - z1.x, z0.y + z1.y);
+        const cf c = cmul(make_float2(-w.y, w.x), dif);
+        st_stream(dst + k, make_float2(sum.x - c.x, sum.y - c.y));
+        st_stream(dst + (M - k), make_float2(sum.x + c.x, -(sum.y + c.y)));
+    };
+    if (!valid) return;
+    static_for<0, B / 2>([&](auto s_) {
+        constexpr int s = decltype(s_)::value;
+        constexpr int A = 2 * s * R, Bk = (2 * s + 1) * R;
+        const int p = j + s * T;
+        if constexpr (s == 0) {
+            // Thread 0's first pair holds butterflies 0 (block A) and STR/2 (block B), which mirror into
+            // themselves: same arithmetic, different operands -- chosen with selects, no divergent branch.
+            const bool self = (j == 0);
+            auto pick = [&](cf a, cf b) { return self ? b : a; };
+            static_for<0, R>([&](auto u_) {
+                constexpr int u = decltype(u_)::value;
+                if constexpr (u < R / 2) {
+                    emit(v[A + u], pick(v[Bk + R - 1 - u], v[A + (R - u) % R]), p + u * STR);     // self: Y[u*STR] (u = 0: Y[0], Y[M])
+                } else {
+                    constexpr int w = u - R / 2;
+                    emit(pick(v[A + u], v[Bk + w]), pick(v[Bk + R - 1 - u], v[Bk + R - 1 - w]),
+                         self ? STR / 2 + w * STR : p + u * STR);
+                }
+            });
+            if (self) {
+                const cf mid = v[A + R / 2];                                         // Z[M/2]
+                st_stream(dst + M / 2, make_float2(2.0f * mid.x, -2.0f * mid.y));
+            }
+        } else {
+            static_for<0, R>([&](auto u_) {
+                constexpr int u = decltype(u_)::value;
+                emit(v[A + u], v[Bk + R - 1 - u], p + u * STR);
+            });
+        }
+    });
+}
+
 // Compile-time description of one kernel variant.
 // PF_ = true: every group owns a dense staging buffer that a bulk asynchronous copy (cp.async.bulk)
 // refills with its NEXT transform while the current one is being computed: the load of item i+1 is in
@@ -273,6 +342,10 @@ struct Cfg {
     static constexpr int T = M / E;
     static constexpr int THREADS = G * T;
     static constexpr int NSTAGE = R2 > 1 ? 3 : 2;
+    static constexpr int RLAST = R2 > 1 ? R2 : R1;
+    // real forward: split in registers on mirror-paired butterflies when the last stage gives a thread >= 2 of them
+    // (measured exception: M = 512 runs faster with the shared-memory split, .93 vs .78 of the copy peak)
+    static constexpr bool PAIRED = MODE_ == MODE_R2C && ((E_ / RLAST) % 2 == 0) && M_ != 512;
     static constexpr int LOGPAD = ilog2(R0);
     static constexpr int XBUF = M + (M >> LOGPAD) + 2;          // complex slots per group (+ slot M for the real modes)
     static constexpr int LUT1 = TWR_ ? 0 : (R1 - 1) * R0;       // stage 1: Ns = R0
@@ -283,7 +356,8 @@ struct Cfg {
     static constexpr int GROUP_SLOTS = XBUF + (PF == PF_DOUBLE ? M : 0);     // exchange buffer (+ staging buffer)
     static constexpr int SMEM_BYTES = 8 * (LUT1 + LUT2 + G * GROUP_SLOTS) + (PF ? 8 * G : 0);
     static_assert(!PF || MODE_ != MODE_C2R, "the half-spectrum rows of C2R are not 16-byte aligned");
-    static_assert(PF != PF_INPLACE || MODE_ == MODE_C2C, "in-place prefetch: the real epilogue still owns the buffer");
+    static_assert(PF != PF_INPLACE || MODE_ == MODE_C2C || (MODE_ == MODE_R2C && (E_ / (R2_ > 1 ? R2_ : R1_)) % 2 == 0 && M_ != 512),
+                  "in-place prefetch: the shared-memory real epilogue still owns the buffer");
     static_assert(!TWR_ || R1_ == E_, "TWR: stage 1 must be one butterfly per thread (m = j mod R0 is loop invariant)");
     static_assert(R0 * R1 * R2 == M, "radices must multiply to the transform length");
     static_assert(R0 <= E && R1 <= E && R2 <= E, "a butterfly must fit one thread");
@@ -334,7 +408,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
     cf twb[TwSplit<R1>::NB];
     if constexpr (C::TWR) load_tw_bases<R1, INV>(twb, p.table, j & (R0 - 1), p.log2_nt - ilog2(R0 * R1));
     cf pw[C::NPOW];
-    if constexpr (C::POW2) load_pow_bases<T, E, R2, INV>(pw, p.table, j, p.log2_nt - ilog2(M));
+    if constexpr (C::POW2) load_pow_bases<M, T, E, R2, INV, C::PAIRED>(pw, p.table, j, p.log2_nt - ilog2(M));
 
     unsigned phase = 0;
     if constexpr (C::PF) {
@@ -399,12 +473,15 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
         group_sync<T>(g);
 
         // ---- stage 1 (Ns = R0) ----
-        stage_gather<M, T, E, R1, LOGPAD, SRC_XBUF>(v, src, xb, j, valid);
+        constexpr bool PAIR1 = C::PAIRED && C::NSTAGE == 2;     // last stage of a two-stage real-forward plan
+        stage_gather<M, T, E, R1, LOGPAD, SRC_XBUF, PAIR1>(v, src, xb, j, valid);
         if constexpr (C::PF == PF_INPLACE && C::NSTAGE == 2) { group_sync<T>(g); issue_next(item); }
         if constexpr (C::TWR) stage_math_regs<E, R1, INV>(v, twb);
-        else                  stage_math<T, E, R1, R0, INV, TW_LUT>(v, lut1, p.table, 0, j);
+        else                  stage_math<T, E, R1, R0, INV, TW_LUT, PAIR1>(v, lut1, p.table, 0, j);
         if constexpr (C::NSTAGE == 2) {
-            if constexpr (MODE == MODE_R2C) {
+            if constexpr (PAIR1) {
+                r2c_paired_epilogue<M, T, E, R1>(v, dst, p.table, sh_real, j, valid);
+            } else if constexpr (MODE == MODE_R2C) {
                 group_sync<T>(g);
                 stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XNAT>(v, dst, xb, j, valid);
             } else {
@@ -415,11 +492,13 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XCHG>(v, dst, xb, j, valid);
             group_sync<T>(g);
             // ---- stage 2 (Ns = R0*R1) ----
-            stage_gather<M, T, E, R2, LOGPAD, SRC_XBUF>(v, src, xb, j, valid);
+            stage_gather<M, T, E, R2, LOGPAD, SRC_XBUF, C::PAIRED>(v, src, xb, j, valid);
             if constexpr (C::PF == PF_INPLACE) { group_sync<T>(g); issue_next(item); }
             if constexpr (C::POW2) stage_math_pow<E, R2, INV>(v, pw);
-            else                   stage_math<T, E, R2, R0 * R1, INV, TW_LUT>(v, lut2, p.table, sh_last, j);
-            if constexpr (MODE == MODE_R2C) {
+            else                   stage_math<T, E, R2, R0 * R1, INV, TW_LUT, C::PAIRED>(v, lut2, p.table, sh_last, j);
+            if constexpr (C::PAIRED) {
+                r2c_paired_epilogue<M, T, E, R2>(v, dst, p.table, sh_real, j, valid);
+            } else if constexpr (MODE == MODE_R2C) {
                 group_sync<T>(g);
                 stage_scatter<M, T, E, R2, R0 * R1, LOGPAD, DST_XNAT>(v, dst, xb, j, valid);
             } else {
@@ -427,7 +506,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             }
         }
 
-        if constexpr (MODE == MODE_R2C) {
+        if constexpr (MODE == MODE_R2C && !C::PAIRED) {
             // split (fft_real_default.cpp:23-62): Y[k] = (Z[k] + conj Z[M-k]) - i W_2M^k (Z[k] - conj Z[M-k]);
             // pairwise with c = f * diff:  Y[k] = sum - c,  Y[M-k] = conj(sum + c);  Z[M] == Z[0].
             group_sync<T>(g);

@@ -91,6 +91,16 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
             default: break;
         }
     }
+#elif CKB_VARIANT == 2
+    if (prefetch_mode() && ((uintptr_t) p.in & 15) == 0 && (p.in_stride & 1) == 0) {
+        switch (M) {
+#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0>>(p, s);
+            CKB_INPLACE_PREFETCH_PLANS_R2C(X)
+#undef X
+            default: break;
+        }
+    }
 #endif
     switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \

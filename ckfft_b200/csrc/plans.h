@@ -37,5 +37,11 @@
     X(2048,  32, 32, 32,  2,  4, 2, 0) \
     X(4096,  32, 32, 32,  4,  2, 2, 0) \
     X(8192,  32, 32, 32,  8,  1, 2, 1)
+// Real-forward in-place prefetch (needs the register split, i.e. an even number of last-stage butterflies).
+#define CKB_INPLACE_PREFETCH_PLANS_R2C(X) \
+    X(2048,  32, 32, 32,  2,  4, 2, 0) \
+    X(4096,  32, 32, 32,  4,  2, 2, 0) \
+    X(8192,  32, 32, 32,  8,  1, 2, 1)
+
 #define CKB_MAX_SINGLE_PASS 16384   /* largest complex length done in one launch */
 #define CKB_MAX_TABLE 32768         /* device twiddle table W_Nt^k covers real n up to this in one pass */
