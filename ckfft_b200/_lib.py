@@ -16,7 +16,8 @@ B200_SYMBOLS = ["CkFftComplexForwardBatch", "CkFftComplexInverseBatch", "CkFftRe
                 "CkFftRealInverseBatch", "CkFftComplexForwardBatchAsync", "CkFftComplexInverseBatchAsync",
                 "CkFftRealForwardBatchAsync", "CkFftRealInverseBatchAsync", "CkFftB200GetPlan",
                 "CkFftB200LastError", "CkFftB200KernelLaunches", "CkFftB200HostAlloc", "CkFftB200HostFree",
-                "CkFftB200ContextDevice"]
+                "CkFftB200ContextDevice", "CkFftB200PackColumnsAsync", "CkFftB200UnpackTransposeAsync",
+                "CkFftB200TwiddleRowsAsync"]
 
 
 class Plan(C.Structure):
@@ -60,5 +61,8 @@ def load() -> C.CDLL:
     lib.CkFftB200HostFree.restype = None
     lib.CkFftB200HostFree.argtypes = [vp]
     lib.CkFftB200ContextDevice.argtypes = [vp]
+    lib.CkFftB200PackColumnsAsync.argtypes = [vp, vp, sz, i, sz, vp]
+    lib.CkFftB200UnpackTransposeAsync.argtypes = [vp, vp, i, sz, sz, vp]
+    lib.CkFftB200TwiddleRowsAsync.argtypes = [vp, i, vp, sz, sz, sz, i, vp]
     _lib = lib
     return lib

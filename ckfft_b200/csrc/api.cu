@@ -650,4 +650,45 @@ void CkFftB200HostFree(void* p)
 
 int CkFftB200ContextDevice(const CkFftContext* c) { return (c && c->magic == kMagic) ? c->device : -1; }
 
+// ---- local steps of the distributed six-step transform (device pointers, stream-ordered) ----
+int CkFftB200PackColumnsAsync(const CkFftComplex* in, CkFftComplex* out, size_t rows, int parts, size_t width, void* stream)
+{
+    if (!in || !out || in == out || parts <= 0) { set_error("pack: bad arguments"); return 0; }
+    if (rows == 0 || width == 0) return 1;
+    cudaError_t e = ckb::launch_pack_columns((const ckb::cf*) in, (ckb::cf*) out, (long long) rows, parts, (long long) width,
+                                             (cudaStream_t) stream);
+    if (e != cudaSuccess) { set_error("pack kernel", e); return 0; }
+    return 1;
+}
+
+int CkFftB200UnpackTransposeAsync(const CkFftComplex* in, CkFftComplex* out, int parts, size_t rowsPerPart, size_t width,
+                                  void* stream)
+{
+    if (!in || !out || in == out || parts <= 0) { set_error("unpack: bad arguments"); return 0; }
+    if (rowsPerPart == 0 || width == 0) return 1;
+    cudaError_t e = ckb::launch_unpack_transpose((const ckb::cf*) in, (ckb::cf*) out, parts, (long long) rowsPerPart,
+                                                 (long long) width, (cudaStream_t) stream);
+    if (e != cudaSuccess) { set_error("unpack kernel", e); return 0; }
+    return 1;
+}
+
+int CkFftB200TwiddleRowsAsync(CkFftContext* c, int n, CkFftComplex* data, size_t rows, size_t cols, size_t firstRow,
+                              int inverse, void* stream)
+{
+    if (!c || c->magic != kMagic) { set_error("invalid context"); return 0; }
+    if (!is_pow2(n) || n > c->maxCount || !c->dTwLo) { set_error("twiddle: n must be a power of two <= nMax of a multi-pass context"); return 0; }
+    if (!data) { set_error("twiddle: NULL data"); return 0; }
+    if (rows == 0 || cols == 0) return 1;
+    if ((unsigned long long) (firstRow + rows - 1) * (unsigned long long) (cols - 1) >= (unsigned long long) n) {
+        set_error("twiddle: (firstRow + rows) * cols exceeds n");
+        return 0;
+    }
+    DeviceGuard guard(c->device);
+    if (!guard.ok) { set_error("cannot select the context's device"); return 0; }
+    cudaError_t e = ckb::launch_twiddle_rows((ckb::cf*) data, (long long) rows, (long long) cols, (long long) firstRow, big_tw(c),
+                                             ilog2i(n), inverse != 0, (cudaStream_t) stream);
+    if (e != cudaSuccess) { set_error("twiddle kernel", e); return 0; }
+    return 1;
+}
+
 }  // extern "C"

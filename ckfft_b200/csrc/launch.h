@@ -31,6 +31,12 @@ cudaError_t launch_real_split(const cf* z, cf* y, int n, long long batch, long l
 cudaError_t launch_real_twist(const cf* y, cf* t, int n, long long batch, long long y_stride, long long t_stride,
                               const BigTwiddles& tw, cudaStream_t s);
 
+// distributed six-step helpers (dist_glue.cu)
+cudaError_t launch_pack_columns(const cf* in, cf* out, long long rows, int parts, long long w, cudaStream_t s);
+cudaError_t launch_unpack_transpose(const cf* in, cf* out, int parts, long long rowsPer, long long w, cudaStream_t s);
+cudaError_t launch_twiddle_rows(cf* data, long long rows, long long cols, long long first_row, const BigTwiddles& tw,
+                                int log2n, bool inverse, cudaStream_t s);
+
 struct PlanRow { int M, E, R0, R1, R2, G, MINB, smem_bytes; };
 const PlanRow* find_plan(int M);      // launch.cu: nullptr if M is not a single-pass length
 

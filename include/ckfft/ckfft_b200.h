@@ -77,6 +77,21 @@ void CkFftB200HostFree(void* p);
 /* device the context is bound to, or -1 */
 int CkFftB200ContextDevice(const CkFftContext* context);
 
+/*
+ * Local steps of the distributed six-step transform of ONE very large 1-D FFT (n = n1*n2 spread over P GPUs,
+ * ckfft_b200/distributed.py).  The exchange between GPUs (all-to-all) is the caller's, these are the
+ * stream-ordered device kernels around it.  Device pointers, out of place unless noted.
+ *   PackColumns:      in[rows][parts][width]          -> out[parts][rows][width]      (slab q goes to peer q)
+ *   UnpackTranspose:  in[parts][rowsPerPart][width]   -> out[width][parts*rowsPerPart]
+ *   TwiddleRows:      data[i][k] *= exp(-+2*pi*i*(firstRow+i)*k/n) in place, i < rows, k < cols;
+ *                     needs a context created with nMax >= n > 16384 and (firstRow+rows)*cols <= n
+ */
+int CkFftB200PackColumnsAsync(const CkFftComplex* in, CkFftComplex* out, size_t rows, int parts, size_t width, void* stream);
+int CkFftB200UnpackTransposeAsync(const CkFftComplex* in, CkFftComplex* out, int parts, size_t rowsPerPart, size_t width,
+                                  void* stream);
+int CkFftB200TwiddleRowsAsync(CkFftContext* context, int n, CkFftComplex* data, size_t rows, size_t cols, size_t firstRow,
+                              int inverse, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

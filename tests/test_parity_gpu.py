@@ -368,3 +368,44 @@ def test_large_host_batch_is_chunked(orc_big):
     pick = [0, 1, 1023, 1024, 1025, 2047, 2048, 2999]
     assert rel_rms(y[pick], orc_big.complex(x[pick])) <= tolerance(n)
     assert rel_rms(y[::97], oracle.fp64_c2c(x[::97])) <= tolerance(n)
+
+
+# ---------------------------------------------------------------------------------------------
+# distributed six-step: the local kernels (pack / tiled transpose / twiddle) on one GPU, world = 1
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("log2n", [16, 21, 24])
+def test_six_step_single_rank(log2n):
+    from ckfft_b200.distributed import DistributedFFT
+
+    n = 1 << log2n
+    rng = np.random.default_rng(log2n)
+    x = uniform_complex(rng, (n,))
+    want = oracle.fp64_c2c(x)
+    d = DistributedFFT(n)
+    xd = torch.from_numpy(x).cuda()
+    y = d.forward(xd)
+    assert rel_rms(y.cpu().numpy(), want) <= tolerance(n)
+    z = d.inverse(y)
+    assert rel_rms(z.cpu().numpy() / n, x) <= tolerance(n)
+    d.close()
+
+
+def test_six_step_glue_kernels():
+    lib = _lib.load()
+    rows, parts, w = 24, 4, 40          # ragged on purpose (not multiples of the 32x32 tile)
+    rng = np.random.default_rng(1)
+    a = uniform_complex(rng, (rows, parts, w))
+    ad = torch.from_numpy(a).cuda()
+    packed = torch.empty_like(ad)
+    assert lib.CkFftB200PackColumnsAsync(ad.data_ptr(), packed.data_ptr(), rows, parts, w, None) == 1
+    assert np.array_equal(packed.cpu().numpy().reshape(parts, rows, w), a.transpose(1, 0, 2))
+    out = torch.empty_like(ad)
+    assert lib.CkFftB200UnpackTransposeAsync(packed.data_ptr(), out.data_ptr(), parts, rows, w, None) == 1
+    assert np.array_equal(out.cpu().numpy().reshape(w, parts * rows), a.transpose(1, 0, 2).transpose(2, 0, 1).reshape(w, parts * rows))
+    n = 1 << 20
+    with ck.Context(n, ck.BOTH) as ctx:
+        t = torch.ones((64, 1024), dtype=torch.complex64, device="cuda")
+        assert lib.CkFftB200TwiddleRowsAsync(ctx.handle, n, t.data_ptr(), 64, 1024, 960, 0, None) == 1
+        i = (960 + np.arange(64))[:, None].astype(np.float64); k = np.arange(1024)[None, :].astype(np.float64)
+        assert np.allclose(t.cpu().numpy(), np.exp(-2j * np.pi * i * k / n), atol=3e-7)
+        assert lib.CkFftB200TwiddleRowsAsync(ctx.handle, n, t.data_ptr(), 64, 1024, 1 << 19, 0, None) == 0   # exponent overflow
