@@ -111,6 +111,32 @@ def build_reference_harness():
     return out
 
 
+def build_b200_harness():
+    """The reference's own harness (regression vs KISS FFT + timing tables), linked against the PRODUCT library:
+    proves the drop-in claim with the reference's own caller.  Needs ckfft_b200/lib/libckfft_b200.so."""
+    os.makedirs(OUT_REF, exist_ok=True)
+    out = os.path.join(OUT_REF, "ckfft_test_b200")
+    root = os.path.dirname(HERE)
+    lib_dir = os.path.join(root, "ckfft_b200", "lib")
+    lib = os.path.join(lib_dir, "libckfft_b200.so")
+    if not os.path.exists(lib):
+        raise FileNotFoundError(lib)
+    compat = os.path.join(HERE, "harness_compat.cpp")
+    srcs = [os.path.join(REF, s) for s in ["src/ckfft/debug.cpp"] + KISS_SOURCES + HARNESS_SOURCES] + [compat]
+    if newer(out, srcs + [lib]):
+        return out
+    with tempfile.TemporaryDirectory() as tmp:
+        objs = []
+        for s in srcs:
+            o = os.path.join(tmp, s.replace("/", "_") + ".o")
+            cc = "gcc" if s.endswith(".c") else "g++"
+            run([cc, "-O2", "-DNDEBUG", "-w", *ref_includes(), "-c", s, "-o", o])
+            objs.append(o)
+        # $ORIGIN-relative rpath: the binary finds the library inside the repo snapshot on the GPU box too
+        run(["g++", "-o", out, *objs, f"-L{lib_dir}", "-lckfft_b200", "-Wl,-rpath,$ORIGIN/../../ckfft_b200/lib", "-lm", "-lrt"])
+    return out
+
+
 def build_fftw():
     os.makedirs(OUT_REF, exist_ok=True)
     out = os.path.join(OUT_REF, "libfftw3_ref.so")
@@ -139,6 +165,10 @@ def build_all(with_fftw=True, with_harness=True, verbose=True):
                 built["harness"] = build_reference_harness()
             except subprocess.CalledProcessError as e:  # harness is optional
                 print("reference harness build failed:", e, file=sys.stderr)
+        try:
+            built["harness_b200"] = build_b200_harness()
+        except (subprocess.CalledProcessError, OSError) as e:
+            print("reference harness (B200 link) build failed:", e, file=sys.stderr)
         if with_fftw:
             try:
                 built["fftw"] = build_fftw()
