@@ -272,6 +272,55 @@ __device__ __forceinline__ void stage_scatter(const cf (&v)[E], cf* __restrict__
     });
 }
 
+// Half exchange (Cfg::HX): the exchange buffer holds ONE float per point; real parts go through it first, then
+// imaginary parts.  Twice the barriers, half the shared memory -- which is what lets the 16384-point kernel keep a
+// second, bulk-prefetched transform resident next to the one being computed.
+template <int M, int T, int E, int R, int NS, int LOGPAD, int COMP>
+__device__ __forceinline__ void half_scatter(const cf (&v)[E], float* xf, int j)
+{
+    constexpr int B = E / R;
+    static_for<0, B>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        const int jq = j + q * T;
+        static_for<0, R>([&](auto u_) {
+            constexpr int u = decltype(u_)::value;
+            const int p = (jq / NS) * (NS * R) + (jq & (NS - 1)) + u * NS;
+            xf[padidx<LOGPAD>(p)] = COMP == 0 ? v[q * R + u].x : v[q * R + u].y;
+        });
+    });
+}
+
+template <int M, int T, int E, int R, int LOGPAD, int COMP>
+__device__ __forceinline__ void half_gather(cf (&v)[E], const float* xf, int j)
+{
+    constexpr int B = E / R, STR = M / R;
+    static_for<0, B>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        const int jq = j + q * T;
+        static_for<0, R>([&](auto t_) {
+            constexpr int t = decltype(t_)::value;
+            constexpr int slot = q * R + bitrev<R>(t);
+            const float f = xf[padidx<LOGPAD>(jq + t * STR)];
+            if constexpr (COMP == 0) v[slot].x = f; else v[slot].y = f;
+        });
+    });
+}
+
+// scatter with the producing stage's geometry (R, NS), barrier, gather with the consuming stage's radix RN
+// (in place in v: once the real parts are scattered their registers are free to receive the gathered ones,
+//  the imaginary parts stay put until their turn)
+template <int M, int T, int E, int R, int NS, int RN, int LOGPAD>
+__device__ __forceinline__ void half_exchange(cf (&v)[E], float* xf, int j, int g)
+{
+    half_scatter<M, T, E, R, NS, LOGPAD, 0>(v, xf, j);
+    group_sync<T>(g);
+    half_gather<M, T, E, RN, LOGPAD, 0>(v, xf, j);
+    group_sync<T>(g);
+    half_scatter<M, T, E, R, NS, LOGPAD, 1>(v, xf, j);
+    group_sync<T>(g);
+    half_gather<M, T, E, RN, LOGPAD, 1>(v, xf, j);
+}
+
 // Real-forward split on a thread's mirror-paired butterflies (see bfly_index).  v holds, per pair slot s,
 // Z[p + u*STR] in block 2s and Z[pbar + u*STR] in block 2s+1 (natural u order).  Writes Y[0 .. M].
 //   Y[k] = (Z[k] + conj Z[M-k]) - i W_2M^k (Z[k] - conj Z[M-k]);  with c = i W^k * diff:
@@ -333,8 +382,10 @@ __device__ __forceinline__ void r2c_paired_epilogue(const cf (&v)[E], cf* __rest
 // last stage's arithmetic and the stores (no extra shared memory, occupancy unchanged).
 enum Prefetch { PF_NONE = 0, PF_DOUBLE = 1, PF_INPLACE = 2 };
 
-template <int M_, int E_, int R0_, int R1_, int R2_, int G_, bool INV_, int MODE_, int MINB_ = 1, int PF_ = PF_NONE, bool TWR_ = false>
+template <int M_, int E_, int R0_, int R1_, int R2_, int G_, bool INV_, int MODE_, int MINB_ = 1, int PF_ = PF_NONE, bool TWR_ = false,
+          bool HX_ = false>
 struct Cfg {
+    static constexpr bool HX = HX_;         // half exchange: one float per point in the exchange buffer (complex mode only)
     static constexpr int PF = PF_;
     static constexpr bool TWR = TWR_;       // stage-1 twiddles from register-resident bases (two-stage plans with R1 == E)
     static constexpr int M = M_, E = E_, R0 = R0_, R1 = R1_, R2 = R2_, G = G_, MODE = MODE_, MINB = MINB_;
@@ -353,7 +404,9 @@ struct Cfg {
     static constexpr bool POW2 = NSTAGE == 3 && !LUT2_SMEM;        // last-stage twiddles from register power bases
     static constexpr int NPOW = POW2 ? (E / R2) * ilog2(R2) : 1;
     static constexpr int LUT2 = LUT2_SMEM ? (R2 - 1) * R0 * R1 : 0;   // stage 2: Ns = R0*R1
-    static constexpr int GROUP_SLOTS = XBUF + (PF == PF_DOUBLE ? M : 0);     // exchange buffer (+ staging buffer)
+    static constexpr int XSLOTS = HX_ ? ((XBUF / 2 + 2) & ~1) : XBUF;        // complex slots of the exchange buffer (even: 16-byte steps)
+    static constexpr int GROUP_SLOTS = XSLOTS + (PF == PF_DOUBLE ? M : 0);   // exchange buffer (+ staging buffer)
+    static_assert(!HX_ || (MODE_ == MODE_C2C && PF_ != PF_INPLACE && R2_ > 1), "half exchange: complex three-stage plans");
     static constexpr int SMEM_BYTES = 8 * (LUT1 + LUT2 + G * GROUP_SLOTS) + (PF ? 8 * G : 0);
     static_assert(!PF || MODE_ != MODE_C2R, "the half-spectrum rows of C2R are not 16-byte aligned");
     static_assert(PF != PF_INPLACE || MODE_ == MODE_C2C || (MODE_ == MODE_R2C && (E_ / (R2_ > 1 ? R2_ : R1_)) % 2 == 0 && M_ != 512),
@@ -379,7 +432,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
     const int g = tid / T;
     const int j = tid % T;
     cf* xb = lut2 + C::LUT2 + g * C::GROUP_SLOTS;
-    cf* inb = C::PF == PF_DOUBLE ? xb + C::XBUF : xb;                  // staging buffer of the bulk copies
+    cf* inb = C::PF == PF_DOUBLE ? xb + C::XSLOTS : xb;                // staging buffer of the bulk copies
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(lut2 + C::LUT2 + G * C::GROUP_SLOTS) + g;
     unsigned long long l2pol = 0;
     if constexpr (C::PF) {
@@ -469,12 +522,15 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             stage_gather<M, T, E, R0, LOGPAD, SRC_GLOBAL>(v, src, xb, j, valid);
         }
         stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j);
-        stage_scatter<M, T, E, R0, 1, LOGPAD, DST_XCHG>(v, dst, xb, j, valid);
-        group_sync<T>(g);
-
-        // ---- stage 1 (Ns = R0) ----
         constexpr bool PAIR1 = C::PAIRED && C::NSTAGE == 2;     // last stage of a two-stage real-forward plan
-        stage_gather<M, T, E, R1, LOGPAD, SRC_XBUF, PAIR1>(v, src, xb, j, valid);
+        if constexpr (C::HX) {
+            half_exchange<M, T, E, R0, 1, R1, LOGPAD>(v, reinterpret_cast<float*>(xb), j, g);
+        } else {
+            stage_scatter<M, T, E, R0, 1, LOGPAD, DST_XCHG>(v, dst, xb, j, valid);
+            group_sync<T>(g);
+            // ---- stage 1 (Ns = R0) ----
+            stage_gather<M, T, E, R1, LOGPAD, SRC_XBUF, PAIR1>(v, src, xb, j, valid);
+        }
         if constexpr (C::PF == PF_INPLACE && C::NSTAGE == 2) { group_sync<T>(g); issue_next(item); }
         if constexpr (C::TWR) stage_math_regs<E, R1, INV>(v, twb);
         else                  stage_math<T, E, R1, R0, INV, TW_LUT, PAIR1>(v, lut1, p.table, 0, j);
@@ -489,10 +545,14 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             }
         } else {
             group_sync<T>(g);
-            stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XCHG>(v, dst, xb, j, valid);
-            group_sync<T>(g);
-            // ---- stage 2 (Ns = R0*R1) ----
-            stage_gather<M, T, E, R2, LOGPAD, SRC_XBUF, C::PAIRED>(v, src, xb, j, valid);
+            if constexpr (C::HX) {
+                half_exchange<M, T, E, R1, R0, R2, LOGPAD>(v, reinterpret_cast<float*>(xb), j, g);
+            } else {
+                stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XCHG>(v, dst, xb, j, valid);
+                group_sync<T>(g);
+                // ---- stage 2 (Ns = R0*R1) ----
+                stage_gather<M, T, E, R2, LOGPAD, SRC_XBUF, C::PAIRED>(v, src, xb, j, valid);
+            }
             if constexpr (C::PF == PF_INPLACE) { group_sync<T>(g); issue_next(item); }
             if constexpr (C::POW2) stage_math_pow<E, R2, INV>(v, pw);
             else                   stage_math<T, E, R2, R0 * R1, INV, TW_LUT, C::PAIRED>(v, lut2, p.table, sh_last, j);

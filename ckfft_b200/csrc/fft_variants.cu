@@ -88,6 +88,10 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
     case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0>>(p, s);
             CKB_INPLACE_PREFETCH_PLANS(X)
 #undef X
+#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_DOUBLE, TWR_ != 0, true>>(p, s);
+            CKB_HALF_EXCHANGE_PLANS(X)
+#undef X
             default: break;
         }
     }

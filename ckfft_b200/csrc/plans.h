@@ -28,6 +28,12 @@
 #define CKB_PREFETCH_PLANS(X) \
     X(1024,  32, 32, 32,  1,  4, 3, 1)
 
+// 16384 points: one transform fills the register file of an SM, so the only way to overlap its HBM traffic with
+// arithmetic is a second, prefetched transform in shared memory: double-buffered bulk prefetch (128 KiB staging)
+// next to a HALF exchange buffer (Cfg::HX, real and imaginary parts exchanged one after the other, 66 KiB).
+#define CKB_HALF_EXCHANGE_PLANS(X) \
+    X(16384, 32, 32, 32, 16,  1, 1, 0)
+
 // In-place prefetch variants (Cfg::PF == PF_INPLACE), complex transforms only.  Measured on B200 (fraction of
 // the 6.55 TB/s copy peak, without -> with): 256 .89->.94, 512 .87->.95, 2048 .90->.95, 4096 .66->.95,
 // 8192 .74->.87; rows shorter than 2 KiB lose (too many tiny bulk copies), 16384 loses (.64->.59).
