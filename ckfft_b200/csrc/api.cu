@@ -275,7 +275,11 @@ int run_host(const _CkFftContext* c, Kind kind, int n, const void* in, void* out
 {
     const size_t ib = in_elems(kind, n) * in_elem_bytes(kind);     // bytes per transform
     const size_t ob = out_elems(kind, n) * out_elem_bytes(kind);
-    const size_t target = size_t(32) << 20;                        // ~32 MiB of input per chunk
+    static const size_t target = [] {                              // input bytes per chunk (default 32 MiB)
+        const char* e = getenv("CKFFT_B200_CHUNK_MB");
+        const long mb = e ? atol(e) : 0;
+        return size_t(mb > 0 && mb <= 4096 ? mb : 32) << 20;
+    }();
     size_t per_chunk = target / ib;
     if (per_chunk < 1) per_chunk = 1;
     if (per_chunk > batch) per_chunk = batch;
