@@ -21,6 +21,7 @@
 // reference's exact fp32 formula (src/ckfft/context.cpp:90-105), so every twiddle used here is
 // bit-identical to the table entry the reference would have used for the same angle.
 #pragma once
+#include <stdint.h>
 #include "fft_regs.cuh"
 
 namespace ckb {
@@ -408,8 +409,8 @@ struct Cfg {
     static constexpr int GROUP_SLOTS = XSLOTS + (PF == PF_DOUBLE ? M : 0);   // exchange buffer (+ staging buffer)
     static_assert(!HX_ || (MODE_ == MODE_C2C && PF_ != PF_INPLACE && R2_ > 1), "half exchange: complex three-stage plans");
     static constexpr int SMEM_BYTES = 8 * (LUT1 + LUT2 + G * GROUP_SLOTS) + (PF ? 8 * G : 0);
-    static_assert(!PF || MODE_ != MODE_C2R, "the half-spectrum rows of C2R are not 16-byte aligned");
-    static_assert(PF != PF_INPLACE || MODE_ == MODE_C2C || (MODE_ == MODE_R2C && (E_ / (R2_ > 1 ? R2_ : R1_)) % 2 == 0 && M_ != 512),
+    static_assert(PF != PF_DOUBLE || MODE_ != MODE_C2R, "C2R prefetches in place (see the C2R prologue)");
+    static_assert(PF != PF_INPLACE || MODE_ != MODE_R2C || ((E_ / (R2_ > 1 ? R2_ : R1_)) % 2 == 0 && M_ != 512),
                   "in-place prefetch: the shared-memory real epilogue still owns the buffer");
     static_assert(!TWR_ || R1_ == E_, "TWR: stage 1 must be one butterfly per thread (m = j mod R0 is loop invariant)");
     static_assert(R0 * R1 * R2 == M, "radices must multiply to the transform length");
@@ -464,24 +465,23 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
     if constexpr (C::POW2) load_pow_bases<M, T, E, R2, INV, C::PAIRED>(pw, p.table, j, p.log2_nt - ilog2(M));
 
     unsigned phase = 0;
-    if constexpr (C::PF) {
-        const long long first = (long long) blockIdx.x * G + g;
-        if (j == 0 && first < p.batch) {
-            mbar_expect_tx(mbar, M * 8);
-            bulk_load(inb, p.in + first * p.in_stride, M * 8, mbar, l2pol);
-        }
-    }
-
     // one thread per group refills the staging buffer with the group's next transform
-    auto issue_next = [&](long long item) {
-        const long long next = item + (long long) gridDim.x * G;
-        if (j == 0 && next < p.batch) {
+    // C2R rows hold M+1 complex values and start on 8-byte boundaries only: the copy starts at the 16-byte boundary
+    // at or below the row and takes M+2 values, so Y[k] lands in slot k + pad (pad = 0 or 1).  The launcher keeps a
+    // last row whose over-copy would leave the array out of this kernel.
+    constexpr unsigned kCopyBytes = (MODE == MODE_C2R ? M + 2 : M) * 8;
+    auto issue_row = [&](long long row) {
+        if (j == 0 && row < p.batch) {
+            const cf* rsrc = p.in + row * p.in_stride;
+            if constexpr (MODE == MODE_C2R) rsrc = reinterpret_cast<const cf*>(reinterpret_cast<uintptr_t>(rsrc) & ~uintptr_t(15));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(mbar, M * 8);
-            bulk_load(inb, p.in + next * p.in_stride, M * 8, mbar, l2pol);
+            mbar_expect_tx(mbar, kCopyBytes);
+            bulk_load(inb, rsrc, kCopyBytes, mbar, l2pol);
         }
     };
+    auto issue_next = [&](long long item) { issue_row(item + (long long) gridDim.x * G); };
     (void) issue_next;
+    if constexpr (C::PF != PF_NONE) issue_row((long long) blockIdx.x * G + g);
 
     for (long long base = (long long) blockIdx.x * G; base < p.batch; base += (long long) gridDim.x * G) {
         const long long item = base + g;
@@ -491,7 +491,30 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
         cf v[E];
 
         // ---- stage 0 (Ns = 1, no twiddles) ----
-        if constexpr (MODE == MODE_C2R) {
+        if constexpr (MODE == MODE_C2R && C::PF == PF_INPLACE) {
+            // The row was bulk-copied into the (dense) buffer; twist it in place -- a thread owns both slots of a
+            // mirror pair -- then gather stage 0 from the dense layout.
+            if (valid) mbar_wait(mbar, phase);
+            phase ^= 1u;
+            cf* yb = xb + ((reinterpret_cast<uintptr_t>(src) >> 3) & 1);        // Y[k] sits in yb[k]
+            static_for<0, E / 2>([&](auto i_) {
+                const int k = j + decltype(i_)::value * T;       // 0 .. M/2-1
+                const cf y0 = yb[k], y1 = yb[M - k];
+                const cf w = __ldg(p.table + (k << sh_real));
+                const cf sum = make_float2(y0.x + y1.x, y0.y - y1.y);
+                const cf dif = make_float2(y0.x - y1.x, y0.y + y1.y);
+                const cf c = cmul(make_float2(w.y, w.x), dif);
+                yb[k] = make_float2(sum.x + c.x, sum.y + c.y);
+                if (k != 0) yb[M - k] = make_float2(sum.x - c.x, -(sum.y - c.y));
+            });
+            if (j == 0) {
+                const cf y = yb[M / 2];
+                yb[M / 2] = make_float2(2.0f * y.x, -2.0f * y.y);
+            }
+            group_sync<T>(g);
+            stage_gather<M, T, E, R0, LOGPAD, SRC_INBUF>(v, src, yb, j, valid);
+            group_sync<T>(g);
+        } else if constexpr (MODE == MODE_C2R) {
             // twist (fft_real_default.cpp:65-111): T[k] = (Y[k] + conj Y[M-k]) + i conj(W_2M^k) (Y[k] - conj Y[M-k]),
             // computed pairwise: with c = f * diff,  T[k] = sum + c,  T[M-k] = conj(sum - c).
             static_for<0, E / 2>([&](auto i_) {

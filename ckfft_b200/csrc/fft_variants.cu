@@ -106,6 +106,40 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
         }
     }
 #endif
+#if CKB_VARIANT == 3
+    if (prefetch_mode() && p.batch > 0 && ((uintptr_t) p.in & 15) == 0) {      // (first row: nothing to read below it)
+        // Rows start on 8-byte boundaries; the kernel copies M+2 values from the 16-byte boundary below each row.
+        // If that would run past the end of the LAST row (its pad is 0 and rows are dense), that row goes to the
+        // plain kernel instead.
+        const uintptr_t last = (uintptr_t) (p.in + (p.batch - 1) * p.in_stride);
+        const bool last_overruns = ((last >> 3) & 1) == 0 && p.in_stride <= M + 1;
+        KernelParams head = p;
+        if (last_overruns) head.batch = p.batch - 1;
+        cudaError_t e = cudaErrorInvalidValue;
+        switch (M) {
+#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
+    case M_: e = launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0>>(head, s); break;
+            CKB_INPLACE_PREFETCH_PLANS_C2R(X)
+#undef X
+            default: break;
+        }
+        if (e == cudaSuccess) {
+            if (!last_overruns) return cudaSuccess;
+            KernelParams tail = p;
+            tail.in = p.in + (p.batch - 1) * p.in_stride;
+            tail.out = p.out + (p.batch - 1) * p.out_stride;
+            tail.batch = 1;
+            switch (M) {
+#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0>>(tail, s);
+                CKB_INPLACE_PREFETCH_PLANS_C2R(X)
+#undef X
+                default: return cudaErrorInvalidValue;
+            }
+        }
+        if (e != cudaErrorInvalidValue) return e;
+    }
+#endif
     switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
     case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0>>(p, s);

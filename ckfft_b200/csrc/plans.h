@@ -49,5 +49,11 @@
     X(4096,  32, 32, 32,  4,  2, 2, 0) \
     X(8192,  32, 32, 32,  8,  1, 2, 1)
 
+// Real-inverse in-place prefetch (rows are bulk-copied from the 16-byte boundary below them, twisted in place).
+#define CKB_INPLACE_PREFETCH_PLANS_C2R(X) \
+    X(2048,  32, 32, 32,  2,  4, 2, 0) \
+    X(4096,  32, 32, 32,  4,  2, 2, 0) \
+    X(8192,  32, 32, 32,  8,  1, 2, 1)
+
 #define CKB_MAX_SINGLE_PASS 16384   /* largest complex length done in one launch */
 #define CKB_MAX_TABLE 32768         /* device twiddle table W_Nt^k covers real n up to this in one pass */
