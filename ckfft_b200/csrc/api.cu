@@ -99,7 +99,21 @@ cudaError_t enqueue(const _CkFftContext* c, Kind kind, int n, const void* in, vo
 
 // ---- multi-pass lengths ---------------------------------------------------------------------
 // Scratch is stream-ordered (cudaMallocAsync / cudaFreeAsync): nothing mutable lives in the context.
-constexpr size_t kScratchCapBytes = size_t(2) << 30;
+constexpr size_t kScratchCapBytes = size_t(2) << 30;      // real-transform glue buffers
+
+// Group size of the multi-pass transforms = size of the stream-ordered scratch array.  Measured on B200: groups
+// small enough for the intermediate to stay in the 126 MB L2 (16-64 MiB) LOSE (.33 -> .22-.30 of the copy peak at
+// 2^15..2^20): the per-group launches are too short to fill the machine.  Default 2 GiB.
+// (CKFFT_B200_L2_GROUP_MB overrides it for measurements.)
+size_t l2_group_bytes()
+{
+    static const size_t bytes = [] {
+        const char* e = getenv("CKFFT_B200_L2_GROUP_MB");
+        const long mb = e ? atol(e) : 0;
+        return size_t(mb > 0 && mb <= 8192 ? mb : 2048) << 20;
+    }();
+    return bytes;
+}
 
 ckb::BigTwiddles big_tw(const _CkFftContext* c) { return ckb::BigTwiddles{ c->dTwLo, c->dTwHi, c->twH, c->log2Tmax }; }
 
@@ -109,7 +123,7 @@ cudaError_t enqueue_large_c2c(const _CkFftContext* c, bool inv, int n, const ckb
     if (!c->dTwLo) return cudaErrorNotSupported;
     if (in_stride != n || out_stride != n) return cudaErrorNotSupported;   // multi-pass path: dense batches only
     const size_t per = (size_t) n * sizeof(ckb::cf);
-    long long sub = (long long) (kScratchCapBytes / per);
+    long long sub = (long long) (l2_group_bytes() / per);
     if (sub < 1) sub = 1;
     if (sub > batch) sub = batch;
     ckb::cf* scratch = nullptr;

@@ -100,7 +100,7 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 
-enum Src { SRC_GLOBAL = 0, SRC_XBUF = 1, SRC_INBUF = 2 };
+enum Src { SRC_GLOBAL = 0, SRC_XBUF = 1, SRC_INBUF = 2, SRC_GLOBAL_KEEP = 3 };   // _KEEP: default cache policy (L2-resident input)
 enum Dst { DST_GLOBAL = 0, DST_XCHG = 1, DST_XNAT = 2 };
 enum Tw { TW_NONE = 0, TW_LUT = 1, TW_TABLE = 2, TW_REGS = 3 };
 
@@ -165,6 +165,8 @@ __device__ __forceinline__ void stage_gather(cf (&v)[E], const cf* __restrict__ 
             constexpr int slot = q * R + bitrev<R>(t);
             if constexpr (SRC == SRC_GLOBAL) {
                 if (valid) v[slot] = ld_stream(gsrc + jq + t * STR);   // an invalid group computes on garbage and stores nothing
+            } else if constexpr (SRC == SRC_GLOBAL_KEEP) {
+                if (valid) v[slot] = __ldg(gsrc + jq + t * STR);
             } else if constexpr (SRC == SRC_INBUF) {
                 v[slot] = xb[jq + t * STR];            // dense staging buffer filled by a bulk copy
             } else {

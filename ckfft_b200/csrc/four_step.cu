@@ -84,18 +84,26 @@ cudaError_t launch_four_step(bool inverse, int log2n, const cf* in, cf* out, cf*
     p.table = table; p.log2_nt = log2_nt;
     p.tw_lo = tw.lo; p.tw_hi = tw.hi; p.tw_h = tw.h;
     cudaError_t e;
+    // Cache policy: the user's input is read once and the final output written once (streaming, evict-first);
+    // intermediates are written with the default policy so that the next pass finds them in the 126 MB L2 -- the
+    // caller keeps `batch` small enough for that (api.cu, enqueue_large_c2c).
     if (npass == 2) {
         p.in = in; p.out = scratch; p.nproblems = batch; p.ncols = L[1]; p.tw_shift = tw.log2_tmax - log2n; p.P = 1; p.Q = 1;
+        p.stream_in = 1; p.stream_out = 0;
         if ((e = launch_pass(inverse, KIND_COLUMN, L[0], p, s)) != cudaSuccess) return e;
         p.in = scratch; p.out = out; p.nproblems = batch; p.ncols = L[0]; p.P = L[0]; p.Q = 1;
+        p.stream_in = 0; p.stream_out = 1;
         return launch_pass(inverse, KIND_LAST, L[1], p, s);
     }
     p.in = in; p.out = out; p.nproblems = batch; p.ncols = (int) (n / L[0]); p.tw_shift = tw.log2_tmax - log2n; p.P = 1; p.Q = 1;
+    p.stream_in = 1; p.stream_out = 0;
     if ((e = launch_pass(inverse, KIND_COLUMN, L[0], p, s)) != cudaSuccess) return e;
     p.in = out; p.out = scratch; p.nproblems = batch * L[0]; p.ncols = L[2];
     p.tw_shift = tw.log2_tmax - ilog2(L[1] * L[2]);
+    p.stream_in = 0; p.stream_out = 0;
     if ((e = launch_pass(inverse, KIND_COLUMN, L[1], p, s)) != cudaSuccess) return e;
     p.in = scratch; p.out = out; p.nproblems = batch; p.ncols = L[0] * L[1]; p.P = L[0]; p.Q = L[1];
+    p.stream_in = 0; p.stream_out = 1;
     return launch_pass(inverse, KIND_LAST, L[2], p, s);
 }
 

@@ -38,7 +38,12 @@ struct TileParams {
     long long nproblems;    // independent problems of TN = L * ncols points, back to back
     int ncols;              // columns per problem
     int P, Q;               // KIND_LAST: input column c starts at ((c % P) * Q + c / P) * L
+    int stream_in;          // 1: the input is read once (ld.global.cs); 0: it was just written by the previous pass and
+    int stream_out;         //    should be found in L2 (default policy).  Same for the output.
 };
+
+__device__ __forceinline__ cf ld_sel(const cf* p, int stream) { return stream ? __ldcs(p) : __ldg(p); }
+__device__ __forceinline__ void st_sel(cf* p, cf v, int stream) { if (stream) __stcs(p, v); else *p = v; }
 
 template <int L_, int E_, int R0_, int R1_, int C_, bool INV_, int KIND_, int MINB_>
 struct TileCfg {
@@ -102,7 +107,7 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
             // row-chunk gather of the [L][C] tile: consecutive lanes read consecutive columns
             static_for<0, E>([&](auto i_) {
                 const int idx = tid + decltype(i_)::value * THREADS;
-                v[decltype(i_)::value] = ld_stream(pin + (long long) (idx / C) * p.ncols + c0 + (idx % C));
+                v[decltype(i_)::value] = ld_sel(pin + (long long) (idx / C) * p.ncols + c0 + (idx % C), p.stream_in);
             });
             static_for<0, E>([&](auto i_) {
                 const int idx = tid + decltype(i_)::value * THREADS;
@@ -114,7 +119,8 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
         } else {
             const int c = c0 + g;
             const cf* src = pin + (long long) ((c % p.P) * p.Q + c / p.P) * L;
-            stage_gather<L, T, E, R0, LOGPAD, SRC_GLOBAL>(v, src, xb, j, true);
+            if (p.stream_in) stage_gather<L, T, E, R0, LOGPAD, SRC_GLOBAL>(v, src, xb, j, true);
+            else             stage_gather<L, T, E, R0, LOGPAD, SRC_GLOBAL_KEEP>(v, src, xb, j, true);
         }
         stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j);
         stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xb, j, true);
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
             const int c = idx % C, k = idx / C;
             cf val = xall[c * XBUF + padidx<LOGPAD>(k)];
             if constexpr (TC::KIND == KIND_COLUMN) val = cmul(val, big_twiddle(p, (unsigned) (c0 + c), (unsigned) k, INV));
-            st_stream(pout + (long long) k * p.ncols + c0 + c, val);
+            st_sel(pout + (long long) k * p.ncols + c0 + c, val, p.stream_out);
         }
         __syncthreads();
     }
