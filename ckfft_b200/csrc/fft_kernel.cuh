@@ -375,6 +375,23 @@ __device__ __forceinline__ void r2c_paired_epilogue(const cf (&v)[E], cf* __rest
     });
 }
 
+// Row-strided global access for the multi-pass tile kernels: butterfly input t of a column lives `rowstride`
+// elements apart (the column is one of C adjacent columns of a [L][ncols] array).
+template <int M, int T, int E, int R>
+__device__ __forceinline__ void gather_rows(cf (&v)[E], const cf* __restrict__ col, long long rowstride, int j, int stream)
+{
+    constexpr int B = E / R, STR = M / R;
+    static_for<0, B>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        const int jq = j + q * T;
+        static_for<0, R>([&](auto t_) {
+            constexpr int t = decltype(t_)::value;
+            const cf* a = col + (long long) (jq + t * STR) * rowstride;
+            v[q * R + bitrev<R>(t)] = stream ? __ldcs(a) : __ldg(a);
+        });
+    });
+}
+
 // Compile-time description of one kernel variant.
 // PF_ = true: every group owns a dense staging buffer that a bulk asynchronous copy (cp.async.bulk)
 // refills with its NEXT transform while the current one is being computed: the load of item i+1 is in

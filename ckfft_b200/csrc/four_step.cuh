@@ -52,6 +52,7 @@ struct TileCfg {
     static constexpr int T = L / E;
     static constexpr int THREADS = C * T;
     static constexpr int LOGPAD = ilog2(R0);
+    static_assert(R1 % 4 == 0, "the inter-pass twiddle factorisation works on groups of four bins");
     static constexpr int XRAW = L + (L >> LOGPAD) + 1;
     static constexpr int XBUF = XRAW | 1;                  // odd: the C columns of a row chunk hit distinct banks
     static constexpr int LUT1 = (R1 - 1) * R0;
@@ -70,6 +71,11 @@ __device__ __forceinline__ cf big_twiddle(const TileParams& p, unsigned c, unsig
     return w;
 }
 
+// Thread maps.  "along the transform": group = tid / T, j = tid % T  (a group's lanes are adjacent: contiguous columns
+// are read with unit stride).  "along the columns": group = tid % C, j = tid / C  (adjacent lanes hold adjacent
+// columns: a warp request covers whole 128-byte row chunks of the [L][ncols] array).  The shared-memory exchange
+// between the two radix stages is where a kernel may switch from one map to the other, so every pass moves its
+// data through shared memory exactly once.
 template <class TC>
 __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileParams p)
 {
@@ -81,9 +87,12 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
     cf* lut1 = reinterpret_cast<cf*>(smem_raw);
     cf* xall = lut1 + TC::LUT1;
     const int tid = threadIdx.x;
-    const int g = tid / T;          // column of the tile owned by this thread's group
-    const int j = tid % T;
-    cf* xb = xall + g * XBUF;
+    // stage 0 map: along the columns for the column pass (strided rows), along the transform for the last pass
+    const int g0 = TC::KIND == KIND_COLUMN ? tid % C : tid / T;
+    const int j0 = TC::KIND == KIND_COLUMN ? tid / C : tid % T;
+    // stage 1 map: always along the columns (the results leave as 128-byte row chunks)
+    const int g1 = tid % C;
+    const int j1 = tid / C;
 
     {
         const int sh1 = p.log2_nt - ilog2(L);
@@ -104,43 +113,51 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
         cf v[E];
 
         if constexpr (TC::KIND == KIND_COLUMN) {
-            // row-chunk gather of the [L][C] tile: consecutive lanes read consecutive columns
-            static_for<0, E>([&](auto i_) {
-                const int idx = tid + decltype(i_)::value * THREADS;
-                v[decltype(i_)::value] = ld_sel(pin + (long long) (idx / C) * p.ncols + c0 + (idx % C), p.stream_in);
-            });
-            static_for<0, E>([&](auto i_) {
-                const int idx = tid + decltype(i_)::value * THREADS;
-                xall[(idx % C) * XBUF + padidx<LOGPAD>(idx / C)] = v[decltype(i_)::value];
-            });
-            __syncthreads();
-            stage_gather<L, T, E, R0, LOGPAD, SRC_XBUF>(v, nullptr, xb, j, true);
-            __syncwarp();
+            gather_rows<L, T, E, R0>(v, pin + c0 + g0, p.ncols, j0, p.stream_in);
         } else {
-            const int c = c0 + g;
+            const int c = c0 + g0;
             const cf* src = pin + (long long) ((c % p.P) * p.Q + c / p.P) * L;
-            if (p.stream_in) stage_gather<L, T, E, R0, LOGPAD, SRC_GLOBAL>(v, src, xb, j, true);
-            else             stage_gather<L, T, E, R0, LOGPAD, SRC_GLOBAL_KEEP>(v, src, xb, j, true);
+            if (p.stream_in) stage_gather<L, T, E, R0, LOGPAD, SRC_GLOBAL>(v, src, nullptr, j0, true);
+            else             stage_gather<L, T, E, R0, LOGPAD, SRC_GLOBAL_KEEP>(v, src, nullptr, j0, true);
         }
-        stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j);
-        stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xb, j, true);
-        __syncwarp();
-        stage_gather<L, T, E, R1, LOGPAD, SRC_XBUF>(v, nullptr, xb, j, true);
-        stage_math<T, E, R1, R0, INV, TW_LUT>(v, lut1, p.table, 0, j);
-        __syncwarp();
-        stage_scatter<L, T, E, R1, R0, LOGPAD, DST_XNAT>(v, nullptr, xb, j, true);
+        stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j0);
+        stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xall + g0 * XBUF, j0, true);
         __syncthreads();
+        stage_gather<L, T, E, R1, LOGPAD, SRC_XBUF>(v, nullptr, xall + g1 * XBUF, j1, true);
+        stage_math<T, E, R1, R0, INV, TW_LUT>(v, lut1, p.table, 0, j1);
 
-        // row-chunk scatter of the transformed tile: output k of column c -> c + ncols * k
-#pragma unroll 4
-        for (int i = 0; i < E; ++i) {
-            const int idx = tid + i * THREADS;
-            const int c = idx % C, k = idx / C;
-            cf val = xall[c * XBUF + padidx<LOGPAD>(k)];
-            if constexpr (TC::KIND == KIND_COLUMN) val = cmul(val, big_twiddle(p, (unsigned) (c0 + c), (unsigned) k, INV));
-            st_sel(pout + (long long) k * p.ncols + c0 + c, val, p.stream_out);
-        }
-        __syncthreads();
+        // Results: this thread holds bins k = jq + u * (L / R1) of column c0 + g1, in natural u order.
+        constexpr int B1 = E / R1, STR1 = L / R1;
+        cf* ocol = pout + c0 + g1;
+        static_for<0, B1>([&](auto q_) {
+            constexpr int q = decltype(q_)::value;
+            const int jq = j1 + q * T;
+            if constexpr (TC::KIND == KIND_COLUMN) {
+                // inter-pass twiddle W_TN^(cc * k), k = jq + u * STR1: geometric in u; with u = 4a + b it factors as
+                // A_a * B_b,  A_a = W^(cc * (jq + 4a*STR1)),  B_b = W^(cc * b*STR1): R1/4 + 3 table look-ups (two
+                // roundings deep) instead of R1.
+                const unsigned cc = (unsigned) (c0 + g1);
+                cf bb[3];
+                static_for<1, 4>([&](auto b_) { constexpr int b = decltype(b_)::value; bb[b - 1] = big_twiddle(p, cc, (unsigned) (b * STR1), INV); });
+                static_for<0, R1 / 4>([&](auto a_) {
+                    constexpr int a = decltype(a_)::value;
+                    const cf aa = big_twiddle(p, cc, (unsigned) (jq + 4 * a * STR1), INV);
+                    static_for<0, 4>([&](auto b_) {
+                        constexpr int b = decltype(b_)::value;
+                        constexpr int u = 4 * a + b;
+                        cf val = cmul(v[q * R1 + u], aa);
+                        if constexpr (b > 0) val = cmul(val, bb[b - 1]);
+                        st_sel(ocol + (long long) (jq + u * STR1) * p.ncols, val, p.stream_out);
+                    });
+                });
+            } else {
+                static_for<0, R1>([&](auto u_) {
+                    constexpr int u = decltype(u_)::value;
+                    st_sel(ocol + (long long) (jq + u * STR1) * p.ncols, v[q * R1 + u], p.stream_out);
+                });
+            }
+        });
+        __syncthreads();     // the next tile's scatter must not overtake this tile's gather
     }
 }
 
