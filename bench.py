@@ -261,6 +261,54 @@ def run_reference_arm(args, spec, rank):
 
 
 # ---------------------------------------------------------------------------------------------
+# config 4 of BASELINE.json: size sweep N = 2^4 .. 2^20, batch = 2^28 / N per GPU (2 GiB in + 2 GiB out)
+# ---------------------------------------------------------------------------------------------
+def run_sweep(args, rank, world, local_rank, dev, barrier):
+    import torch
+    import torch.distributed as dist
+
+    import ckfft_b200 as ck
+
+    peak, peak_src = measured_peak()
+    total = 1 << 28
+    x = torch.view_as_complex(torch.empty((total, 2), dtype=torch.float32, device=dev).uniform_(-1, 1))
+    y = torch.empty_like(x)
+    rows = []
+    steps = max(3, min(args.steps, 20))
+    for lg in range(4, 21):
+        n = 1 << lg
+        ctx = ck.Context(n, ck.FORWARD)
+        xv, yv = x.view(total // n, n), y.view(total // n, n)
+        for _ in range(3):
+            ctx.complex_forward(xv, yv)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ctx.complex_forward(xv, yv)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        gbs = 16.0 * total * world / ms / 1e6
+        rows.append({"n": n, "ms": round(ms, 4), "gbs": round(gbs, 1), "frac_per_gpu": round(gbs / world / peak, 4),
+                     "gflops": round(5.0 * total * lg * world / ms / 1e6, 1)})
+        ctx.close()
+    if rank == 0:
+        mean = sum(r["gbs"] for r in rows) / len(rows)
+        print(json.dumps({
+            "metric": "Batched fp32 C2C FFT HBM GB/s, size sweep N=2^4..2^20 (mean over sizes)", "value": round(mean, 1), "unit": "GB/s",
+            "n_gpus": world, "steps": steps, "warmup": 3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "size sweep, batch = 2^28/N complex transforms per GPU (2 GiB in + 2 GiB out), forward",
+                       "parallelism": f"batch-sharded x{world}, no collective", "peak": peak, "peak_source": peak_src},
+            "sweep": rows}), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def main():
@@ -279,7 +327,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    spec = workload_spec(args.workload)
+    spec = workload_spec("c2c1024" if args.workload == "sweep" else args.workload)
 
     if args.impl == "reference":
         run_reference_arm(args, spec, rank)
@@ -303,6 +351,11 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
+    if args.workload == "sweep":
+        run_sweep(args, rank, world, local_rank, dev, barrier)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     n, batch, kind = spec["n"], spec["batch"], spec["kind"]
     sampler = ClockSampler(local_rank) if rank == 0 else None     # started early: nvidia-smi needs ~1 s to come up
     ctx = ck.Context(n, ck.BOTH)
