@@ -267,7 +267,9 @@ struct Staging
         }
         return cudaSuccess;
     }
-    ~Staging() { /* process teardown: the driver reclaims device memory; cudaFree here could run after CUDA shutdown */ }
+    // A worker thread that exits gives its staging buffers back.  (At process teardown the runtime may already be
+    // gone; the calls then fail harmlessly and the driver reclaims the memory.)
+    ~Staging() { release(); cudaGetLastError(); }
 };
 thread_local Staging tl_staging;
 
