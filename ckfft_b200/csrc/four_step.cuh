@@ -20,6 +20,7 @@
 // Inter-pass twiddles are W_Tmax^e with e up to 2^30: a full table is out of the question, so the context
 // carries a two-level table built in double precision, W^e = hi[e >> h] * lo[e & (2^h - 1)].
 #pragma once
+#include <cuda.h>          // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include "fft_kernel.cuh"
 
 namespace ckb {
@@ -45,8 +46,14 @@ struct TileParams {
 __device__ __forceinline__ cf ld_sel(const cf* p, int stream) { return stream ? __ldcs(p) : __ldg(p); }
 __device__ __forceinline__ void st_sel(cf* p, cf v, int stream) { if (stream) __stcs(p, v); else *p = v; }
 
-template <int L_, int E_, int R0_, int R1_, int C_, bool INV_, int KIND_, int MINB_>
+// PFT_ = true: the tile is staged by the TMA unit and prefetched.  Column pass: the [L][C] tile (rows ncols apart
+// in global memory) is fetched with cp.async.bulk.tensor.2d boxes described by a CUtensorMap; last pass: each of
+// the C contiguous columns with a 1-D cp.async.bulk.  The copy of the NEXT tile is issued as soon as the second
+// radix stage has gathered its inputs, i.e. it overlaps that stage's arithmetic, the inter-pass twiddles and the
+// stores; it lands in the same shared-memory buffer the exchange uses (no extra shared memory).
+template <int L_, int E_, int R0_, int R1_, int C_, bool INV_, int KIND_, int MINB_, bool PFT_ = false>
 struct TileCfg {
+    static constexpr bool PFT = PFT_;
     static constexpr int L = L_, E = E_, R0 = R0_, R1 = R1_, C = C_, KIND = KIND_, MINB = MINB_;
     static constexpr bool INV = INV_;
     static constexpr int T = L / E;
@@ -56,7 +63,9 @@ struct TileCfg {
     static constexpr int XRAW = L + (L >> LOGPAD) + 1;
     static constexpr int XBUF = XRAW | 1;                  // odd: the C columns of a row chunk hit distinct banks
     static constexpr int LUT1 = (R1 - 1) * R0;
-    static constexpr int SMEM_BYTES = 8 * (LUT1 + C * XBUF);
+    static constexpr int SMEM_BYTES = 8 * (LUT1 + C * XBUF) + (PFT_ ? 16 : 0);
+    static constexpr int BOX_ROWS = L < 256 ? L : 256;         // TMA boxes are at most 256 elements per dimension
+    static_assert((LUT1 * 8) % 128 == 0, "the tile buffer must start on a 128-byte boundary for the tensor copies");
     static_assert(R0 * R1 == L && T <= 32 && THREADS <= 1024, "tile plan");
     static_assert((L * C) % THREADS == 0 && (L * C) / THREADS == E, "one tile = E elements per thread");
 };
@@ -76,16 +85,24 @@ __device__ __forceinline__ cf big_twiddle(const TileParams& p, unsigned c, unsig
 // columns: a warp request covers whole 128-byte row chunks of the [L][ncols] array).  The shared-memory exchange
 // between the two radix stages is where a kernel may switch from one map to the other, so every pass moves its
 // data through shared memory exactly once.
+// one 2-D box of a tiled tensor map -> shared memory; completion is signalled on `bar`
+__device__ __forceinline__ void tensor_load_2d(void* dst, const CUtensorMap* map, int x, int y, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
 template <class TC>
-__global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileParams p)
+__global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileParams p, const __grid_constant__ CUtensorMap tmap_in)
 {
     constexpr int L = TC::L, E = TC::E, T = TC::T, C = TC::C, R0 = TC::R0, R1 = TC::R1;
     constexpr int LOGPAD = TC::LOGPAD, XBUF = TC::XBUF, THREADS = TC::THREADS;
     constexpr bool INV = TC::INV;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cf* lut1 = reinterpret_cast<cf*>(smem_raw);
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    cf* lut1 = reinterpret_cast<cf*>(tile_smem);
     cf* xall = lut1 + TC::LUT1;
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(xall + C * XBUF);
     const int tid = threadIdx.x;
     // stage 0 map: along the columns for the column pass (strided rows), along the transform for the last pass
     const int g0 = TC::KIND == KIND_COLUMN ? tid % C : tid / T;
@@ -99,11 +116,40 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
         for (int i = tid; i < TC::LUT1; i += THREADS)
             lut1[i] = table_w(p.table, ((i / R0 + 1) * (i % R0)) << sh1, INV);
     }
+    unsigned long long l2pol = 0;
+    if constexpr (TC::PFT) {
+        if (tid == 0) mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        l2pol = l2_evict_first_policy();
+    }
     __syncthreads();
 
     const int blocks_per_problem = p.ncols / C;
     const long long ntiles = p.nproblems * blocks_per_problem;
     const long long tn = (long long) L * p.ncols;
+
+    // thread 0 asks the TMA unit for a whole tile: dense [L][C] (column pass) or [C][L] (last pass) in `xall`
+    auto issue_tile = [&](long long t) {
+        if (tid != 0 || t >= ntiles) return;
+        const long long prob = t / blocks_per_problem;
+        const int c0 = (int) (t % blocks_per_problem) * C;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(mbar, L * C * 8);
+        if constexpr (TC::KIND == KIND_COLUMN) {
+#pragma unroll
+            for (int r0 = 0; r0 < L; r0 += TC::BOX_ROWS)
+                tensor_load_2d(xall + r0 * C, &tmap_in, c0, (int) (prob * L + r0), mbar);
+        } else {
+            const cf* pin = p.in + prob * tn;
+#pragma unroll
+            for (int g = 0; g < C; ++g) {
+                const int c = c0 + g;
+                bulk_load(xall + g * L, pin + (long long) ((c % p.P) * p.Q + c / p.P) * L, L * 8, mbar, l2pol);
+            }
+        }
+    };
+    unsigned phase = 0;
+    if constexpr (TC::PFT) issue_tile(blockIdx.x);
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long prob = tile / blocks_per_problem;
@@ -112,7 +158,21 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
         cf* __restrict__ pout = p.out + prob * tn;
         cf v[E];
 
-        if constexpr (TC::KIND == KIND_COLUMN) {
+        if constexpr (TC::PFT) {
+            mbar_wait(mbar, phase);
+            phase ^= 1u;
+            constexpr int B0 = E / R0, STR0 = L / R0;
+            static_for<0, B0>([&](auto q_) {
+                constexpr int q = decltype(q_)::value;
+                const int jq = j0 + q * T;
+                static_for<0, R0>([&](auto t_) {
+                    constexpr int t = decltype(t_)::value;
+                    const int row = jq + t * STR0;
+                    v[q * R0 + bitrev<R0>(t)] = TC::KIND == KIND_COLUMN ? xall[row * C + g0] : xall[g0 * L + row];
+                });
+            });
+            __syncthreads();        // the staged tile is consumed: the buffer now serves the exchange
+        } else if constexpr (TC::KIND == KIND_COLUMN) {
             gather_rows<L, T, E, R0>(v, pin + c0 + g0, p.ncols, j0, p.stream_in);
         } else {
             const int c = c0 + g0;
@@ -124,6 +184,10 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
         stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xall + g0 * XBUF, j0, true);
         __syncthreads();
         stage_gather<L, T, E, R1, LOGPAD, SRC_XBUF>(v, nullptr, xall + g1 * XBUF, j1, true);
+        if constexpr (TC::PFT) {
+            __syncthreads();        // exchange consumed: the buffer is free for the next tile
+            issue_tile(tile + gridDim.x);
+        }
         stage_math<T, E, R1, R0, INV, TW_LUT>(v, lut1, p.table, 0, j1);
 
         // Results: this thread holds bins k = jq + u * (L / R1) of column c0 + g1, in natural u order.
@@ -157,7 +221,7 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
                 });
             }
         });
-        __syncthreads();     // the next tile's scatter must not overtake this tile's gather
+        if constexpr (!TC::PFT) __syncthreads();     // the next tile's scatter must not overtake this tile's gather
     }
 }
 
