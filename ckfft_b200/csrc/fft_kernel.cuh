@@ -102,7 +102,7 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
 
 enum Src { SRC_GLOBAL = 0, SRC_XBUF = 1, SRC_INBUF = 2, SRC_GLOBAL_KEEP = 3 };   // _KEEP: default cache policy (L2-resident input)
 enum Dst { DST_GLOBAL = 0, DST_XCHG = 1, DST_XNAT = 2 };
-enum Tw { TW_NONE = 0, TW_LUT = 1, TW_TABLE = 2, TW_REGS = 3 };
+enum Tw { TW_NONE = 0, TW_LUT = 1 };   // register-resident twiddles have their own stage functions (TWR, power bases)
 
 // TW_REGS: the stage twiddles W^(t*m), t = a*LO + b, are rebuilt from LO-1 + HI-1 table values that the
 // thread keeps in registers for the whole kernel:  W^(t*m) = W^(a*LO*m) * W^(b*m)  (one extra rounding on
@@ -241,10 +241,7 @@ __device__ __forceinline__ void stage_math(cf (&v)[E], const cf* lut, const cf* 
             static_for<1, R>([&](auto t_) {
                 constexpr int t = decltype(t_)::value;
                 constexpr int slot = q * R + bitrev<R>(t);
-                cf w;
-                if constexpr (TW == TW_LUT) w = lut[(t - 1) * NS + m];
-                else                        w = table_w(table, (t * m) << tshift, INV);
-                v[slot] = cmul(v[slot], w);
+                v[slot] = cmul(v[slot], lut[(t - 1) * NS + m]);
             });
         });
     }
