@@ -26,7 +26,7 @@ LIB = os.path.join(PKG, "lib", "libckfft_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-fvisibility=default",
-          f"-I{os.path.join(ROOT, 'include')}", f"-I{CSRC}"]
+          f"-I{os.path.join(ROOT, 'include')}", f"-I{CSRC}", *os.environ.get("CKFFT_B200_NVCC_FLAGS", "").split()]
 
 # (object name, source, extra flags)
 UNITS = [
