@@ -272,55 +272,6 @@ __device__ __forceinline__ void stage_scatter(const cf (&v)[E], cf* __restrict__
     });
 }
 
-// Half exchange (Cfg::HX): the exchange buffer holds ONE float per point; real parts go through it first, then
-// imaginary parts.  Twice the barriers, half the shared memory -- which is what lets the 16384-point kernel keep a
-// second, bulk-prefetched transform resident next to the one being computed.
-template <int M, int T, int E, int R, int NS, int LOGPAD, int COMP>
-__device__ __forceinline__ void half_scatter(const cf (&v)[E], float* xf, int j)
-{
-    constexpr int B = E / R;
-    static_for<0, B>([&](auto q_) {
-        constexpr int q = decltype(q_)::value;
-        const int jq = j + q * T;
-        static_for<0, R>([&](auto u_) {
-            constexpr int u = decltype(u_)::value;
-            const int p = (jq / NS) * (NS * R) + (jq & (NS - 1)) + u * NS;
-            xf[padidx<LOGPAD>(p)] = COMP == 0 ? v[q * R + u].x : v[q * R + u].y;
-        });
-    });
-}
-
-template <int M, int T, int E, int R, int LOGPAD, int COMP>
-__device__ __forceinline__ void half_gather(cf (&v)[E], const float* xf, int j)
-{
-    constexpr int B = E / R, STR = M / R;
-    static_for<0, B>([&](auto q_) {
-        constexpr int q = decltype(q_)::value;
-        const int jq = j + q * T;
-        static_for<0, R>([&](auto t_) {
-            constexpr int t = decltype(t_)::value;
-            constexpr int slot = q * R + bitrev<R>(t);
-            const float f = xf[padidx<LOGPAD>(jq + t * STR)];
-            if constexpr (COMP == 0) v[slot].x = f; else v[slot].y = f;
-        });
-    });
-}
-
-// scatter with the producing stage's geometry (R, NS), barrier, gather with the consuming stage's radix RN
-// (in place in v: once the real parts are scattered their registers are free to receive the gathered ones,
-//  the imaginary parts stay put until their turn)
-template <int M, int T, int E, int R, int NS, int RN, int LOGPAD>
-__device__ __forceinline__ void half_exchange(cf (&v)[E], float* xf, int j, int g)
-{
-    half_scatter<M, T, E, R, NS, LOGPAD, 0>(v, xf, j);
-    group_sync<T>(g);
-    half_gather<M, T, E, RN, LOGPAD, 0>(v, xf, j);
-    group_sync<T>(g);
-    half_scatter<M, T, E, R, NS, LOGPAD, 1>(v, xf, j);
-    group_sync<T>(g);
-    half_gather<M, T, E, RN, LOGPAD, 1>(v, xf, j);
-}
-
 // Real-forward split on a thread's mirror-paired butterflies (see bfly_index).  v holds, per pair slot s,
 // Z[p + u*STR] in block 2s and Z[pbar + u*STR] in block 2s+1 (natural u order).  Writes Y[0 .. M].
 //   Y[k] = (Z[k] + conj Z[M-k]) - i W_2M^k (Z[k] - conj Z[M-k]);  with c = i W^k * diff:
@@ -397,12 +348,15 @@ __device__ __forceinline__ void gather_rows(cf (&v)[E], const cf* __restrict__ c
 // PF_ = 2: same idea without the second buffer: the bulk copy of the next transform lands in the exchange
 // buffer itself as soon as the last gather of the current transform has drained it, so it overlaps the
 // last stage's arithmetic and the stores (no extra shared memory, occupancy unchanged).
-enum Prefetch { PF_NONE = 0, PF_DOUBLE = 1, PF_INPLACE = 2 };
+//
+// PF_ = 3 (PF_SPLIT), 16384 points: one transform fills an SM's register file, so its successor can only wait in
+// shared memory, and a full second row (128 KiB) does not fit next to the exchange buffer (135 KiB).  The row is
+// prefetched in two halves: the lower half into a staging buffer of its own as soon as stage 0 has gathered (in
+// flight for the whole transform), the upper half into the exchange buffer once the last stage has gathered.
+enum Prefetch { PF_NONE = 0, PF_DOUBLE = 1, PF_INPLACE = 2, PF_SPLIT = 3 };
 
-template <int M_, int E_, int R0_, int R1_, int R2_, int G_, bool INV_, int MODE_, int MINB_ = 1, int PF_ = PF_NONE, bool TWR_ = false,
-          bool HX_ = false>
+template <int M_, int E_, int R0_, int R1_, int R2_, int G_, bool INV_, int MODE_, int MINB_ = 1, int PF_ = PF_NONE, bool TWR_ = false>
 struct Cfg {
-    static constexpr bool HX = HX_;         // half exchange: one float per point in the exchange buffer (complex mode only)
     static constexpr int PF = PF_;
     static constexpr bool TWR = TWR_;       // stage-1 twiddles from register-resident bases (two-stage plans with R1 == E)
     static constexpr int M = M_, E = E_, R0 = R0_, R1 = R1_, R2 = R2_, G = G_, MODE = MODE_, MINB = MINB_;
@@ -421,10 +375,11 @@ struct Cfg {
     static constexpr bool POW2 = NSTAGE == 3 && !LUT2_SMEM;        // last-stage twiddles from register power bases
     static constexpr int NPOW = POW2 ? (E / R2) * ilog2(R2) : 1;
     static constexpr int LUT2 = LUT2_SMEM ? (R2 - 1) * R0 * R1 : 0;   // stage 2: Ns = R0*R1
-    static constexpr int XSLOTS = HX_ ? ((XBUF / 2 + 2) & ~1) : XBUF;        // complex slots of the exchange buffer (even: 16-byte steps)
-    static constexpr int GROUP_SLOTS = XSLOTS + (PF == PF_DOUBLE ? M : 0);   // exchange buffer (+ staging buffer)
-    static_assert(!HX_ || (MODE_ == MODE_C2C && PF_ != PF_INPLACE && R2_ > 1), "half exchange: complex three-stage plans");
-    static constexpr int SMEM_BYTES = 8 * (LUT1 + LUT2 + G * GROUP_SLOTS) + (PF ? 8 * G : 0);
+    static constexpr int XSLOTS = XBUF;                                      // complex slots of the exchange buffer
+    static constexpr int GROUP_SLOTS = XSLOTS + (PF == PF_DOUBLE ? M : (PF == PF_SPLIT ? M / 2 : 0));   // exchange (+ staging) buffer
+    static_assert(PF_ != PF_SPLIT || (R2_ > 1 && (MODE_ == MODE_C2C || (MODE_ == MODE_R2C && (E_ / R2_) % 2 == 0))),
+                  "split prefetch: three-stage plans whose last stage leaves the exchange buffer idle");
+    static constexpr int SMEM_BYTES = 8 * (LUT1 + LUT2 + G * GROUP_SLOTS) + (PF ? 16 * G : 0);   // + two mbarriers per group
     static_assert(PF != PF_DOUBLE || MODE_ != MODE_C2R, "C2R prefetches in place (see the C2R prologue)");
     static_assert(PF != PF_INPLACE || MODE_ != MODE_R2C || ((E_ / (R2_ > 1 ? R2_ : R1_)) % 2 == 0 && M_ != 512),
                   "in-place prefetch: the shared-memory real epilogue still owns the buffer");
@@ -449,11 +404,12 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
     const int g = tid / T;
     const int j = tid % T;
     cf* xb = lut2 + C::LUT2 + g * C::GROUP_SLOTS;
-    cf* inb = C::PF == PF_DOUBLE ? xb + C::XSLOTS : xb;                // staging buffer of the bulk copies
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(lut2 + C::LUT2 + G * C::GROUP_SLOTS) + g;
+    cf* inb = (C::PF == PF_DOUBLE || C::PF == PF_SPLIT) ? xb + C::XSLOTS : xb;     // staging buffer of the bulk copies
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(lut2 + C::LUT2 + G * C::GROUP_SLOTS) + 2 * g;
+    unsigned long long* mbar_hi = mbar + 1;                             // PF_SPLIT: barrier of the upper half row
     unsigned long long l2pol = 0;
     if constexpr (C::PF) {
-        if (j == 0) mbar_init(mbar, 1);
+        if (j == 0) { mbar_init(mbar, 1); mbar_init(mbar_hi, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         l2pol = l2_evict_first_policy();
     }
@@ -503,7 +459,19 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
     };
     auto issue_next = [&](long long item) { issue_row(item + (long long) gridDim.x * G); };
     (void) issue_next;
-    if constexpr (C::PF != PF_NONE) issue_row((long long) blockIdx.x * G + g);
+    // PF_SPLIT: half 0 = points [0, M/2) -> staging buffer, half 1 = points [M/2, M) -> exchange buffer
+    auto issue_half = [&](long long row, int half) {
+        if (j == 0 && row < p.batch) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(half ? mbar_hi : mbar, M * 4);
+            bulk_load(half ? xb : inb, p.in + row * p.in_stride + half * (M / 2), M * 4, half ? mbar_hi : mbar, l2pol);
+        }
+    };
+    (void) issue_half;
+    if constexpr (C::PF == PF_SPLIT) {
+        issue_half((long long) blockIdx.x * G + g, 0);
+        issue_half((long long) blockIdx.x * G + g, 1);
+    } else if constexpr (C::PF != PF_NONE) issue_row((long long) blockIdx.x * G + g);
 
     for (long long base = (long long) blockIdx.x * G; base < p.batch; base += (long long) gridDim.x * G) {
         const long long item = base + g;
@@ -557,6 +525,16 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             group_sync<T>(g);
             stage_gather<M, T, E, R0, LOGPAD, SRC_XBUF>(v, src, xb, j, valid);
             group_sync<T>(g);
+        } else if constexpr (C::PF == PF_SPLIT) {
+            static_assert(E == R0, "one stage-0 butterfly per thread");
+            if (valid) { mbar_wait(mbar, phase); mbar_wait(mbar_hi, phase); }
+            phase ^= 1u;
+            static_for<0, R0>([&](auto t_) {
+                constexpr int t = decltype(t_)::value;
+                v[bitrev<R0>(t)] = t < R0 / 2 ? inb[j + t * T] : xb[j + (t - R0 / 2) * T];
+            });
+            group_sync<T>(g);                      // both halves are in registers
+            issue_half(item + (long long) gridDim.x * G, 0);
         } else if constexpr (C::PF != PF_NONE) {
             if (valid) mbar_wait(mbar, phase);
             phase ^= 1u;
@@ -568,14 +546,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
         }
         stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j);
         constexpr bool PAIR1 = C::PAIRED && C::NSTAGE == 2;     // last stage of a two-stage real-forward plan
-        if constexpr (C::HX) {
-            half_exchange<M, T, E, R0, 1, R1, LOGPAD>(v, reinterpret_cast<float*>(xb), j, g);
-        } else {
-            stage_scatter<M, T, E, R0, 1, LOGPAD, DST_XCHG>(v, dst, xb, j, valid);
-            group_sync<T>(g);
-            // ---- stage 1 (Ns = R0) ----
-            stage_gather<M, T, E, R1, LOGPAD, SRC_XBUF, PAIR1>(v, src, xb, j, valid);
-        }
+        stage_scatter<M, T, E, R0, 1, LOGPAD, DST_XCHG>(v, dst, xb, j, valid);
+        group_sync<T>(g);
+        // ---- stage 1 (Ns = R0) ----
+        stage_gather<M, T, E, R1, LOGPAD, SRC_XBUF, PAIR1>(v, src, xb, j, valid);
         if constexpr (C::PF == PF_INPLACE && C::NSTAGE == 2) { group_sync<T>(g); issue_next(item); }
         if constexpr (C::TWR) stage_math_regs<E, R1, INV>(v, twb);
         else                  stage_math<T, E, R1, R0, INV, TW_LUT, PAIR1>(v, lut1, p.table, 0, j);
@@ -590,15 +564,12 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             }
         } else {
             group_sync<T>(g);
-            if constexpr (C::HX) {
-                half_exchange<M, T, E, R1, R0, R2, LOGPAD>(v, reinterpret_cast<float*>(xb), j, g);
-            } else {
-                stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XCHG>(v, dst, xb, j, valid);
-                group_sync<T>(g);
-                // ---- stage 2 (Ns = R0*R1) ----
-                stage_gather<M, T, E, R2, LOGPAD, SRC_XBUF, C::PAIRED>(v, src, xb, j, valid);
-            }
+            stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XCHG>(v, dst, xb, j, valid);
+            group_sync<T>(g);
+            // ---- stage 2 (Ns = R0*R1) ----
+            stage_gather<M, T, E, R2, LOGPAD, SRC_XBUF, C::PAIRED>(v, src, xb, j, valid);
             if constexpr (C::PF == PF_INPLACE) { group_sync<T>(g); issue_next(item); }
+            if constexpr (C::PF == PF_SPLIT) { group_sync<T>(g); issue_half(item + (long long) gridDim.x * G, 1); }
             if constexpr (C::POW2) stage_math_pow<E, R2, INV>(v, pw);
             else                   stage_math<T, E, R2, R0 * R1, INV, TW_LUT, C::PAIRED>(v, lut2, p.table, sh_last, j);
             if constexpr (C::PAIRED) {
@@ -635,7 +606,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
         }
         // the next iteration's first scatter must not overtake this iteration's last gather
         // (the in-place prefetch already put a group barrier behind that gather)
-        if constexpr (C::PF != PF_INPLACE) group_sync<T>(g);
+        if constexpr (C::PF != PF_INPLACE && C::PF != PF_SPLIT) group_sync<T>(g);
     }
 }
 

@@ -89,8 +89,8 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
             CKB_INPLACE_PREFETCH_PLANS(X)
 #undef X
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_DOUBLE, TWR_ != 0, true>>(p, s);
-            CKB_HALF_EXCHANGE_PLANS(X)
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_SPLIT, TWR_ != 0>>(p, s);
+            CKB_SPLIT_PREFETCH_PLANS(X)
 #undef X
             default: break;
         }
@@ -101,6 +101,10 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
     case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0>>(p, s);
             CKB_INPLACE_PREFETCH_PLANS_R2C(X)
+#undef X
+#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_SPLIT, TWR_ != 0>>(p, s);
+            CKB_SPLIT_PREFETCH_PLANS(X)
 #undef X
             default: break;
         }

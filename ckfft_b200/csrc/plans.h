@@ -28,10 +28,11 @@
 #define CKB_PREFETCH_PLANS(X) \
     X(1024,  32, 32, 32,  1,  4, 3, 1)
 
-// 16384 points: one transform fills the register file of an SM, so the only way to overlap its HBM traffic with
-// arithmetic is a second, prefetched transform in shared memory: double-buffered bulk prefetch (128 KiB staging)
-// next to a HALF exchange buffer (Cfg::HX, real and imaginary parts exchanged one after the other, 66 KiB).
-#define CKB_HALF_EXCHANGE_PLANS(X) \
+// 16384 points (Cfg::PF == PF_SPLIT): one transform fills the register file of an SM, so the only way to overlap
+// its HBM traffic with arithmetic is a prefetched successor in shared memory; a whole second row does not fit next to
+// the exchange buffer, so the row is prefetched in two halves (see fft_kernel.cuh).  0.64 -> 0.70 of the copy peak.
+// (A half-width exchange buffer -- real parts, then imaginary parts -- with a full staged row measured 0.67.)
+#define CKB_SPLIT_PREFETCH_PLANS(X) \
     X(16384, 32, 32, 32, 16,  1, 1, 0)
 
 // In-place prefetch variants (Cfg::PF == PF_INPLACE), complex transforms only.  Measured on B200 (fraction of
