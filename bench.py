@@ -52,6 +52,8 @@ def workload_spec(name: str):
         n, batch, kind = 4096, 1 << 18, "r2c"
     elif name == "c2r4096":
         n, batch, kind = 4096, 1 << 18, "c2r"
+    elif name == "stft4096":
+        n, batch, kind = 4096, 1 << 18, "pow"       # audio front end: window + R2C + power spectrum
     elif name.startswith("c2c"):
         n, kind = int(name[3:]), "c2c"
         batch = max(1, (1 << 28) // n)          # config 4: constant 2 GiB in + 2 GiB out
@@ -59,11 +61,14 @@ def workload_spec(name: str):
         raise SystemExit(f"unknown workload {name}")
     if kind == "c2c":
         nbytes, flops = 16 * n, 5.0 * n * np.log2(n)
+    elif kind == "pow":
+        nbytes, flops = 4 * n + 4 * (n // 2 + 1), 2.5 * n * np.log2(n)
     else:
         nbytes, flops = 4 * n + 8 * (n // 2 + 1), 2.5 * n * np.log2(n)
     desc = {"c2c": f"batched complex C2C forward N={n} x {batch} transforms fp32 per GPU",
             "r2c": f"batched real R2C N={n} x {batch} frames fp32 per GPU",
-            "c2r": f"batched real C2R N={n} x {batch} frames fp32 per GPU"}[kind]
+            "c2r": f"batched real C2R N={n} x {batch} frames fp32 per GPU",
+            "pow": f"Hann window + R2C + power spectrum N={n} x {batch} frames fp32 per GPU (fused)"}[kind]
     return dict(name=name, kind=kind, n=n, batch=batch, bytes=nbytes, flops=flops, desc=desc)
 
 
@@ -368,6 +373,12 @@ def main():
         x = torch.empty((batch, n), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g)
         y = torch.empty((batch, n // 2 + 1), dtype=torch.complex64, device=dev)
         step = lambda: ctx.real_forward(x, y)      # noqa: E731
+    elif kind == "pow":
+        x = torch.empty((batch, n), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g)
+        wnd = torch.hann_window(n, periodic=True, dtype=torch.float32, device=dev)
+        y = torch.empty((batch, n // 2 + 1), dtype=torch.float32, device=dev)
+        step = lambda: ctx.real_forward_power(x, wnd, y)   # noqa: E731
+        args.no_e2e = True     # device-resident API only
     else:
         x = torch.view_as_complex(torch.empty((batch, n // 2 + 1, 2), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g))
         y = torch.empty((batch, n), dtype=torch.float32, device=dev)
@@ -454,7 +465,8 @@ def main():
         peak, peak_src = measured_peak()
         per_gpu = gbs / world
         line = {
-            "metric": METRIC, "value": round(gbs, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if spec["name"] == "c2c1024" else f"Batched fp32 {kind} FFT HBM GB/s + GFLOP/s at N={n}",
+            "value": round(gbs, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "gflops": round(gflops, 1), "gflops_convention": "5*N*log2(N) per complex transform (2.5*N*log2(N) real)",
@@ -471,7 +483,7 @@ def main():
         }
         if e2e is not None:
             line["e2e"] = e2e
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and kind != "pow":
             line["cpu_baseline"] = cpu_baseline(spec)
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -17,7 +17,7 @@ B200_SYMBOLS = ["CkFftComplexForwardBatch", "CkFftComplexInverseBatch", "CkFftRe
                 "CkFftRealForwardBatchAsync", "CkFftRealInverseBatchAsync", "CkFftB200GetPlan",
                 "CkFftB200LastError", "CkFftB200KernelLaunches", "CkFftB200HostAlloc", "CkFftB200HostFree",
                 "CkFftB200ContextDevice", "CkFftB200PackColumnsAsync", "CkFftB200UnpackTransposeAsync",
-                "CkFftB200TwiddleRowsAsync"]
+                "CkFftB200TwiddleRowsAsync", "CkFftB200RealForwardPowerBatchAsync"]
 
 
 class Plan(C.Structure):
@@ -64,5 +64,6 @@ def load() -> C.CDLL:
     lib.CkFftB200PackColumnsAsync.argtypes = [vp, vp, sz, i, sz, vp]
     lib.CkFftB200UnpackTransposeAsync.argtypes = [vp, vp, i, sz, sz, vp]
     lib.CkFftB200TwiddleRowsAsync.argtypes = [vp, i, vp, sz, sz, sz, i, vp]
+    lib.CkFftB200RealForwardPowerBatchAsync.argtypes = [vp, i, vp, vp, vp, sz, sz, sz, vp]
     _lib = lib
     return lib

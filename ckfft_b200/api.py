@@ -149,6 +149,29 @@ class Context:
             out = self._empty_like(x, tuple(x.shape[:-1]) + (n // 2 + 1,), np.complex64, "complex64")
         return self._run("CkFftRealForward", n, x, out, batch)
 
+    def real_forward_power(self, x, window=None, out=None):
+        """Fused audio front end: |CkFftRealForward(window * x)|^2, float32[..., n] -> float32[..., n/2+1].
+        CUDA tensors only (stream-ordered on torch's current stream)."""
+        import torch
+
+        x = self._prep(x, np.float32, "float32")
+        if not _is_torch(x):
+            raise CkFftError("real_forward_power works on CUDA tensors")
+        n = x.shape[-1]
+        batch = int(np.prod(x.shape[:-1], dtype=np.int64)) if x.ndim > 1 else 1
+        if window is not None:
+            window = self._prep(window, np.float32, "float32")
+            if tuple(window.shape) != (n,):
+                raise CkFftError(f"window must have {n} samples")
+        if out is None:
+            out = torch.empty(tuple(x.shape[:-1]) + (n // 2 + 1,), dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        ok = self._lib.CkFftB200RealForwardPowerBatchAsync(self._ctx, n, x.data_ptr(), window.data_ptr() if window is not None else None,
+                                                           out.data_ptr(), batch, 0, 0, stream)
+        if not ok:
+            self._fail("CkFftB200RealForwardPowerBatchAsync")
+        return out
+
     def real_inverse(self, y, n: int, out=None):
         """CkFftRealInverse: complex64[..., n/2+1] -> float32[..., n]."""
         y = self._prep(y, np.complex64, "complex64")

@@ -38,6 +38,7 @@ UNITS = [
     ("c2c_inv.o", "fft_variants.cu", ["-DCKB_VARIANT=1"]),
     ("r2c.o", "fft_variants.cu", ["-DCKB_VARIANT=2"]),
     ("c2r.o", "fft_variants.cu", ["-DCKB_VARIANT=3"]),
+    ("r2c_audio.o", "fft_variants.cu", ["-DCKB_VARIANT=4"]),
 ]
 
 

@@ -670,6 +670,29 @@ void CkFftB200HostFree(void* p)
 
 int CkFftB200ContextDevice(const CkFftContext* c) { return (c && c->magic == kMagic) ? c->device : -1; }
 
+// ---- audio front end: window, real forward transform and power spectrum in one kernel ----
+int CkFftB200RealForwardPowerBatchAsync(CkFftContext* c, int n, const float* in, const float* window, float* power,
+                                        size_t batch, size_t inStride, size_t outStride, void* stream)
+{
+    if (!check_call(c, K_R2C, n, in, power)) return 0;
+    if (n < 32 || n > c->tableCount) { set_error("power spectrum: n must be 32 .. 32768"); return 0; }
+    if (batch == 0) return 1;
+    if (inStride == 0) inStride = (size_t) n;
+    if (outStride == 0) outStride = (size_t) n / 2 + 1;
+    if (inStride < (size_t) n || outStride < (size_t) n / 2 + 1 || (inStride & 1)) {
+        set_error("power spectrum: strides must cover a frame and the input stride must be even");
+        return 0;
+    }
+    if ((((uintptr_t) in | (uintptr_t) window) & 7) || ((uintptr_t) power & 3)) { set_error("power spectrum: misaligned pointer"); return 0; }
+    DeviceGuard guard(c->device);
+    if (!guard.ok) { set_error("cannot select the context's device"); return 0; }
+    ckb::KernelParams p{ (const ckb::cf*) in, (ckb::cf*) power, c->dTable, c->log2Table, (long long) batch,
+                         (long long) inStride / 2, (long long) outStride, (const ckb::cf*) window };
+    cudaError_t e = ckb::launch_r2c_audio(n / 2, p, (cudaStream_t) stream);
+    if (e != cudaSuccess) { set_error("kernel launch", e); return 0; }
+    return 1;
+}
+
 // ---- local steps of the distributed six-step transform (device pointers, stream-ordered) ----
 int CkFftB200PackColumnsAsync(const CkFftComplex* in, CkFftComplex* out, size_t rows, int parts, size_t width, void* stream)
 {

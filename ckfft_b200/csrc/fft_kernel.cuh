@@ -35,7 +35,8 @@ struct KernelParams {
     int log2_nt;         // log2(Nt)
     long long batch;
     long long in_stride;   // distance between consecutive transforms, in 8-byte units
-    long long out_stride;
+    long long out_stride;  // (AUDIO kernels: the output is a float array and this stride is in floats)
+    const cf* window;      // AUDIO kernels: analysis window, n floats viewed as M complex, or nullptr
 };
 
 template <int LOGPAD> __device__ __forceinline__ int padidx(int p) { return p + (p >> LOGPAD); }
@@ -272,11 +273,20 @@ __device__ __forceinline__ void stage_scatter(const cf (&v)[E], cf* __restrict__
     });
 }
 
+// Where a real-forward kernel puts bin k: the complex value, or -- AUDIO kernels (what an audio caller
+// of CkFftRealForward does next) -- its squared magnitude into a float array, which halves the bytes written.
+template <bool AUDIO>
+__device__ __forceinline__ void put_bin(cf* __restrict__ dst, int k, cf y)
+{
+    if constexpr (AUDIO) __stcs(reinterpret_cast<float*>(dst) + k, fmaf(y.x, y.x, y.y * y.y));
+    else                 st_stream(dst + k, y);
+}
+
 // Real-forward split on a thread's mirror-paired butterflies (see bfly_index).  v holds, per pair slot s,
 // Z[p + u*STR] in block 2s and Z[pbar + u*STR] in block 2s+1 (natural u order).  Writes Y[0 .. M].
 //   Y[k] = (Z[k] + conj Z[M-k]) - i W_2M^k (Z[k] - conj Z[M-k]);  with c = i W^k * diff:
 //   Y[k] = sum - c,  Y[M-k] = conj(sum + c)          (the two statements of fft_real_default.cpp:30-58)
-template <int M, int T, int E, int R>
+template <int M, int T, int E, int R, bool AUDIO>
 __device__ __forceinline__ void r2c_paired_epilogue(const cf (&v)[E], cf* __restrict__ dst, const cf* __restrict__ table,
                                                     int sh_real, int j, bool valid)
 {
@@ -287,8 +297,8 @@ __device__ __forceinline__ void r2c_paired_epilogue(const cf (&v)[E], cf* __rest
         const cf sum = make_float2(z0.x + z1.x, z0.y - z1.y);
         const cf dif = make_float2(z0.x - z1.x, z0.y + z1.y);
         const cf c = cmul(make_float2(-w.y, w.x), dif);
-        st_stream(dst + k, make_float2(sum.x - c.x, sum.y - c.y));
-        st_stream(dst + (M - k), make_float2(sum.x + c.x, -(sum.y + c.y)));
+        put_bin<AUDIO>(dst, k, make_float2(sum.x - c.x, sum.y - c.y));
+        put_bin<AUDIO>(dst, M - k, make_float2(sum.x + c.x, -(sum.y + c.y)));
     };
     if (!valid) return;
     static_for<0, B / 2>([&](auto s_) {
@@ -312,7 +322,7 @@ __device__ __forceinline__ void r2c_paired_epilogue(const cf (&v)[E], cf* __rest
             });
             if (self) {
                 const cf mid = v[A + R / 2];                                         // Z[M/2]
-                st_stream(dst + M / 2, make_float2(2.0f * mid.x, -2.0f * mid.y));
+                put_bin<AUDIO>(dst, M / 2, make_float2(2.0f * mid.x, -2.0f * mid.y));
             }
         } else {
             static_for<0, R>([&](auto u_) {
@@ -355,8 +365,11 @@ __device__ __forceinline__ void gather_rows(cf (&v)[E], const cf* __restrict__ c
 // flight for the whole transform), the upper half into the exchange buffer once the last stage has gathered.
 enum Prefetch { PF_NONE = 0, PF_DOUBLE = 1, PF_INPLACE = 2, PF_SPLIT = 3 };
 
-template <int M_, int E_, int R0_, int R1_, int R2_, int G_, bool INV_, int MODE_, int MINB_ = 1, int PF_ = PF_NONE, bool TWR_ = false>
+template <int M_, int E_, int R0_, int R1_, int R2_, int G_, bool INV_, int MODE_, int MINB_ = 1, int PF_ = PF_NONE, bool TWR_ = false,
+          bool AUDIO_ = false>
 struct Cfg {
+    static constexpr bool AUDIO = AUDIO_;   // real forward with a fused analysis window (load) and power spectrum (store)
+    static_assert(!AUDIO_ || MODE_ == MODE_R2C, "the audio front end is a real-forward kernel");
     static constexpr int PF = PF_;
     static constexpr bool TWR = TWR_;       // stage-1 twiddles from register-resident bases (two-stage plans with R1 == E)
     static constexpr int M = M_, E = E_, R0 = R0_, R1 = R1_, R2 = R2_, G = G_, MODE = MODE_, MINB = MINB_;
@@ -477,7 +490,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
         const long long item = base + g;
         const bool valid = item < p.batch;
         const cf* __restrict__ src = p.in + item * p.in_stride;
-        cf* __restrict__ dst = p.out + item * p.out_stride;
+        cf* __restrict__ dst = C::AUDIO ? reinterpret_cast<cf*>(reinterpret_cast<float*>(p.out) + item * p.out_stride)
+                                        : p.out + item * p.out_stride;
         cf v[E];
 
         // ---- stage 0 (Ns = 1, no twiddles) ----
@@ -544,6 +558,18 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
         } else {
             stage_gather<M, T, E, R0, LOGPAD, SRC_GLOBAL>(v, src, xb, j, valid);
         }
+        if constexpr (C::AUDIO) {
+            // analysis window fused into the load: sample pair (2e, 2e+1) is complex element e of the row
+            if (p.window != nullptr) {
+                static_assert(E == R0, "one stage-0 butterfly per thread");
+                static_for<0, R0>([&](auto t_) {
+                    constexpr int t = decltype(t_)::value;
+                    const cf w = __ldg(p.window + j + t * T);
+                    v[bitrev<R0>(t)].x *= w.x;
+                    v[bitrev<R0>(t)].y *= w.y;
+                });
+            }
+        }
         stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j);
         constexpr bool PAIR1 = C::PAIRED && C::NSTAGE == 2;     // last stage of a two-stage real-forward plan
         stage_scatter<M, T, E, R0, 1, LOGPAD, DST_XCHG>(v, dst, xb, j, valid);
@@ -555,7 +581,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
         else                  stage_math<T, E, R1, R0, INV, TW_LUT, PAIR1>(v, lut1, p.table, 0, j);
         if constexpr (C::NSTAGE == 2) {
             if constexpr (PAIR1) {
-                r2c_paired_epilogue<M, T, E, R1>(v, dst, p.table, sh_real, j, valid);
+                r2c_paired_epilogue<M, T, E, R1, C::AUDIO>(v, dst, p.table, sh_real, j, valid);
             } else if constexpr (MODE == MODE_R2C) {
                 group_sync<T>(g);
                 stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XNAT>(v, dst, xb, j, valid);
@@ -573,7 +599,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             if constexpr (C::POW2) stage_math_pow<E, R2, INV>(v, pw);
             else                   stage_math<T, E, R2, R0 * R1, INV, TW_LUT, C::PAIRED>(v, lut2, p.table, sh_last, j);
             if constexpr (C::PAIRED) {
-                r2c_paired_epilogue<M, T, E, R2>(v, dst, p.table, sh_real, j, valid);
+                r2c_paired_epilogue<M, T, E, R2, C::AUDIO>(v, dst, p.table, sh_real, j, valid);
             } else if constexpr (MODE == MODE_R2C) {
                 group_sync<T>(g);
                 stage_scatter<M, T, E, R2, R0 * R1, LOGPAD, DST_XNAT>(v, dst, xb, j, valid);
@@ -595,13 +621,13 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
                 const cf dif = make_float2(z0.x - z1.x, z0.y + z1.y);
                 const cf c = cmul(make_float2(-w.y, w.x), dif);
                 if (valid) {
-                    st_stream(dst + k, make_float2(sum.x - c.x, sum.y - c.y));
-                    st_stream(dst + (M - k), make_float2(sum.x + c.x, -(sum.y + c.y)));
+                    put_bin<C::AUDIO>(dst, k, make_float2(sum.x - c.x, sum.y - c.y));
+                    put_bin<C::AUDIO>(dst, M - k, make_float2(sum.x + c.x, -(sum.y + c.y)));
                 }
             });
             if (j == 0 && valid) {
                 const cf z = xb[padidx<LOGPAD>(M / 2)];
-                st_stream(dst + M / 2, make_float2(2.0f * z.x, -2.0f * z.y));
+                put_bin<C::AUDIO>(dst, M / 2, make_float2(2.0f * z.x, -2.0f * z.y));
             }
         }
         // the next iteration's first scatter must not overtake this iteration's last gather

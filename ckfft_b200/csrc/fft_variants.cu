@@ -1,16 +1,17 @@
 // fft_variants.cu -- instantiates the single-pass kernel family for ONE (direction, mode) variant.
-// Compiled four times (-DCKB_VARIANT=0..3) so the heavy template instantiations build in parallel:
+// Compiled five times (-DCKB_VARIANT=0..4) so the heavy template instantiations build in parallel:
 //   0  complex forward   (CkFftComplexForward,  reference src/ckfft/ckfft.cpp:78-95)
 //   1  complex inverse   (CkFftComplexInverse,  :97-114)
 //   2  real forward      (CkFftRealForward,     :36-53)   half-length forward FFT + fused split
 //   3  real inverse      (CkFftRealInverse,     :55-76)   fused twist + half-length inverse FFT
+//   4  audio front end   (no reference counterpart) window * frame -> real forward -> |Y|^2
 #include "launch.h"
 #include "plans.h"
 #include <stdint.h>
 #include <stdlib.h>
 
 #ifndef CKB_VARIANT
-#error "compile with -DCKB_VARIANT=0..3"
+#error "compile with -DCKB_VARIANT=0..4"
 #endif
 
 namespace ckb {
@@ -24,10 +25,14 @@ static constexpr bool kInv = true; static constexpr int kMode = MODE_C2C;
 #elif CKB_VARIANT == 2
 #define CKB_FN launch_r2c
 static constexpr bool kInv = false; static constexpr int kMode = MODE_R2C;
-#else
+#elif CKB_VARIANT == 3
 #define CKB_FN launch_c2r
 static constexpr bool kInv = true; static constexpr int kMode = MODE_C2R;
+#else
+#define CKB_FN launch_r2c_audio
+static constexpr bool kInv = false; static constexpr int kMode = MODE_R2C;
 #endif
+static constexpr bool kAudio = CKB_VARIANT == 4;
 
 static int prefetch_mode()
 {
@@ -74,7 +79,7 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
     if (prefetch_mode() && ((uintptr_t) p.in & 15) == 0 && (p.in_stride & 1) == 0) {
         switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_DOUBLE, TWR_ != 0>>(p, s);
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_DOUBLE, TWR_ != 0, kAudio>>(p, s);
             CKB_PREFETCH_PLANS(X)
 #undef X
             default: break;
@@ -85,25 +90,25 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
     if (prefetch_mode() && ((uintptr_t) p.in & 15) == 0 && (p.in_stride & 1) == 0) {
         switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0>>(p, s);
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0, kAudio>>(p, s);
             CKB_INPLACE_PREFETCH_PLANS(X)
 #undef X
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_SPLIT, TWR_ != 0>>(p, s);
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_SPLIT, TWR_ != 0, kAudio>>(p, s);
             CKB_SPLIT_PREFETCH_PLANS(X)
 #undef X
             default: break;
         }
     }
-#elif CKB_VARIANT == 2
+#elif CKB_VARIANT == 2 || CKB_VARIANT == 4
     if (prefetch_mode() && ((uintptr_t) p.in & 15) == 0 && (p.in_stride & 1) == 0) {
         switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0>>(p, s);
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0, kAudio>>(p, s);
             CKB_INPLACE_PREFETCH_PLANS_R2C(X)
 #undef X
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_SPLIT, TWR_ != 0>>(p, s);
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_SPLIT, TWR_ != 0, kAudio>>(p, s);
             CKB_SPLIT_PREFETCH_PLANS(X)
 #undef X
             default: break;
@@ -122,7 +127,7 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
         cudaError_t e = cudaErrorInvalidValue;
         switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: e = launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0>>(head, s); break;
+    case M_: e = launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0, kAudio>>(head, s); break;
             CKB_INPLACE_PREFETCH_PLANS_C2R(X)
 #undef X
             default: break;
@@ -135,7 +140,7 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
             tail.batch = 1;
             switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0>>(tail, s);
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0, kAudio>>(tail, s);
                 CKB_INPLACE_PREFETCH_PLANS_C2R(X)
 #undef X
                 default: return cudaErrorInvalidValue;
@@ -146,7 +151,7 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
 #endif
     switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0>>(p, s);
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0, kAudio>>(p, s);
         CKB_SINGLE_PASS_PLANS(X)
 #undef X
         default: return cudaErrorInvalidValue;

@@ -10,6 +10,7 @@ cudaError_t launch_c2c_fwd(int M, const KernelParams& p, cudaStream_t s);
 cudaError_t launch_c2c_inv(int M, const KernelParams& p, cudaStream_t s);
 cudaError_t launch_r2c(int M, const KernelParams& p, cudaStream_t s);
 cudaError_t launch_c2r(int M, const KernelParams& p, cudaStream_t s);
+cudaError_t launch_r2c_audio(int M, const KernelParams& p, cudaStream_t s);   // window + real forward + power spectrum
 
 // tiny sizes (tiny.cu)
 cudaError_t launch_tiny_c2c(int n, bool inverse, const KernelParams& p, cudaStream_t s);

@@ -47,6 +47,17 @@ int CkFftRealForwardBatchAsync(CkFftContext* context, int n, const float* input,
 int CkFftRealInverseBatchAsync(CkFftContext* context, int n, const CkFftComplex* input, float* output,
                                size_t batch, size_t inStride, size_t outStride, void* stream);
 
+/*
+ * Audio front end: what a caller of CkFftRealForward on audio frames does next, fused into the transform kernel.
+ *   power[b][k] = | CkFftRealForward(window .* input[b]) [k] |^2 ,  k = 0 .. n/2      (= 4 |rfft(w x)|^2)
+ * `window` (n floats, device memory) may be NULL for a rectangular window.  The window is applied while the frame
+ * is loaded and only the n/2+1 powers are written (floats), so a frame costs 4n + 4(n/2+1) bytes of HBM traffic
+ * instead of the 3 x that of separate window / transform / magnitude passes.  32 <= n <= 32768, device pointers,
+ * stream-ordered; strides in floats (0 = dense), the input stride must be even.
+ */
+int CkFftB200RealForwardPowerBatchAsync(CkFftContext* context, int n, const float* input, const float* window, float* power,
+                                        size_t batch, size_t inStride, size_t outStride, void* stream);
+
 /* How the library will run a transform of n points (host-side planner, no GPU needed). */
 typedef struct
 {

@@ -409,3 +409,25 @@ def test_six_step_glue_kernels():
         i = (960 + np.arange(64))[:, None].astype(np.float64); k = np.arange(1024)[None, :].astype(np.float64)
         assert np.allclose(t.cpu().numpy(), np.exp(-2j * np.pi * i * k / n), atol=3e-7)
         assert lib.CkFftB200TwiddleRowsAsync(ctx.handle, n, t.data_ptr(), 64, 1024, 1 << 19, 0, None) == 0   # exponent overflow
+
+
+# ---------------------------------------------------------------------------------------------
+# audio front end: window + real forward + power spectrum fused in one kernel
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [32, 64, 256, 1024, 2048, 4096, 8192, 32768])
+def test_power_spectrum_vs_oracle(ctx_big, orc_big, n):
+    rng = np.random.default_rng(n + 7)
+    for batch in (1, 5, 34):
+        if n * batch > (1 << 19):
+            continue
+        x = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+        w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n) / n)).astype(np.float32)     # Hann
+        for window in (None, w):
+            xw = x if window is None else (x * window).astype(np.float32)
+            y = orc_big.real_forward(xw)
+            want = (y.real.astype(np.float64) ** 2 + y.imag.astype(np.float64) ** 2)
+            got = ctx_big.real_forward_power(torch.from_numpy(x).cuda(),
+                                             None if window is None else torch.from_numpy(window).cuda()).cpu().numpy()
+            assert got.shape == (batch, n // 2 + 1)
+            # power = |Y|^2: relative error doubles; measured against the spectrum's total power
+            assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 4 * tolerance(n), (n, batch)
