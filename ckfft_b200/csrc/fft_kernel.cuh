@@ -8,18 +8,26 @@
 // Structure (Stockham autosort, 2 or 3 radix stages, no bit-reversal pass):
 //   * a "group" of T = M/E threads owns one transform; every thread keeps E complex values in
 //     registers; G groups share a CTA;  CTAs are persistent and walk the batch grid-stride;
-//   * stage s loads x[j + t*M/R], multiplies by the stage twiddle W_{Ns*R}^{t*(j mod Ns)} taken
-//     from a shared-memory LUT laid out [t][j mod Ns] (immediate-offset, conflict-free LDS.64),
-//     runs an R-point register DFT (fft_regs.cuh) and scatters to (j/Ns)*Ns*R + (j mod Ns) + u*Ns;
-//   * the first stage reads global memory directly (every warp request is a run of contiguous
-//     8-byte elements: T*8 bytes per group, 256 B per warp when T >= 32), the last stage writes it
-//     the same way; stages in between exchange through a padded shared-memory buffer
-//     (index p -> p + p/R0: conflict-free for the stride-R0 scatter and for the unit-stride gather);
-//   * groups of <= 32 threads synchronise with __syncwarp only, larger groups with a named barrier.
+//   * stage s loads x[j + t*M/R], multiplies by the stage twiddle W_{Ns*R}^{t*(j mod Ns)}, runs an R-point
+//     register DFT (fft_regs.cuh) and scatters to (j/Ns)*Ns*R + (j mod Ns) + u*Ns.  Twiddles come from a
+//     shared-memory LUT laid out [t][j mod Ns] (immediate-offset, conflict-free LDS.64) or, where the plan
+//     says so (TWR, power bases), from a few table values the thread keeps in registers for the whole kernel;
+//   * stages exchange through a padded shared-memory buffer (index p -> p + p/R0: conflict-free for the
+//     stride-R0 scatter and for the unit-stride gather); groups of <= 32 threads synchronise with __syncwarp
+//     only, larger groups with a named barrier;
+//   * global input: every row is one contiguous run of M*8 bytes.  The prefetching variants (Cfg::PF) have
+//     one elected thread per group fetch the group's NEXT row with a bulk asynchronous copy (cp.async.bulk,
+//     TMA's 1-D mode, completion on an mbarrier) while the current row is being transformed; the plain variant
+//     gathers straight into registers (256 contiguous bytes per warp request when T >= 32);
+//   * global output: the last stage scatters X[j + u*M/R] straight from registers, again in runs of
+//     contiguous 8-byte elements per warp request.
+//   * real transforms: the split (R2C) runs on mirror-paired butterflies in registers or through the exchange
+//     buffer, the twist (C2R) in shared memory before stage 0 -- no extra pass over HBM, no tmpBuf traffic.
 //
 // Twiddle values come from the context's device table W_Nt^k, which the host fills with the
 // reference's exact fp32 formula (src/ckfft/context.cpp:90-105), so every twiddle used here is
-// bit-identical to the table entry the reference would have used for the same angle.
+// bit-identical to the table entry the reference would have used for the same angle (or a product of at
+// most log2(R) such entries).
 #pragma once
 #include <stdint.h>
 #include "fft_regs.cuh"
@@ -105,7 +113,7 @@ enum Src { SRC_GLOBAL = 0, SRC_XBUF = 1, SRC_INBUF = 2, SRC_GLOBAL_KEEP = 3 };  
 enum Dst { DST_GLOBAL = 0, DST_XCHG = 1, DST_XNAT = 2 };
 enum Tw { TW_NONE = 0, TW_LUT = 1 };   // register-resident twiddles have their own stage functions (TWR, power bases)
 
-// TW_REGS: the stage twiddles W^(t*m), t = a*LO + b, are rebuilt from LO-1 + HI-1 table values that the
+// TWR: the stage twiddles W^(t*m), t = a*LO + b, are rebuilt from LO-1 + HI-1 table values that the
 // thread keeps in registers for the whole kernel:  W^(t*m) = W^(a*LO*m) * W^(b*m)  (one extra rounding on
 // the products, none on the bases).  Removes the per-transform LUT traffic from the shared-memory port.
 template <int R> struct TwSplit {
@@ -221,7 +229,7 @@ __device__ __forceinline__ void stage_math_pow(cf (&v)[E], const cf (&pw)[(E / R
 template <int E, int R, bool INV>
 __device__ __forceinline__ void stage_math_regs(cf (&v)[E], const cf (&twb)[TwSplit<R>::NB])
 {
-    static_assert(E == R, "TW_REGS needs one butterfly per thread");
+    static_assert(E == R, "TWR needs one butterfly per thread");
     static_for<1, R>([&](auto t_) {
         constexpr int t = decltype(t_)::value;
         constexpr int slot = bitrev<R>(t);
