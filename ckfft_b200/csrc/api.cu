@@ -285,6 +285,53 @@ Side classify(const void* p, int dev)
     return SIDE_HOST;   // unregistered or pinned host memory
 }
 
+// Small host calls (the classic single-transform use of the reference, src/test/test.cpp:254-301): the data goes
+// through a per-thread pinned, device-mapped bounce buffer and the kernel works on that host memory directly over
+// PCIe (the bulk copies and the stores address it like any global memory).  One launch and one stream
+// synchronisation instead of two staged copies: 23 us -> ~10 us for one 1024-point transform.
+constexpr size_t kSmallCallBytes = size_t(256) << 10;
+
+struct Bounce
+{
+    void* in = nullptr;
+    void* out = nullptr;
+    bool tried = false;
+    bool ensure()
+    {
+        if (!tried) {
+            tried = true;
+            if (cudaHostAlloc(&in, kSmallCallBytes, cudaHostAllocMapped) != cudaSuccess) in = nullptr;
+            if (cudaHostAlloc(&out, kSmallCallBytes, cudaHostAllocMapped) != cudaSuccess) out = nullptr;
+            cudaGetLastError();
+        }
+        return in && out;
+    }
+    ~Bounce() { if (in) cudaFreeHost(in); if (out) cudaFreeHost(out); cudaGetLastError(); }
+};
+thread_local Bounce tl_bounce;
+
+// returns 1 done, 0 failed, -1 not applicable (caller takes the chunked path)
+int run_host_small(const _CkFftContext* c, Kind kind, int n, const void* in, void* out, size_t batch)
+{
+    const size_t ib = in_elems(kind, n) * in_elem_bytes(kind) * batch;
+    const size_t ob = out_elems(kind, n) * out_elem_bytes(kind) * batch;
+    if (ib > kSmallCallBytes || ob > kSmallCallBytes || n > CKB_MAX_SINGLE_PASS) return -1;
+    Bounce& b = tl_bounce;
+    if (!b.ensure()) return -1;
+    void *din = nullptr, *dout = nullptr;
+    if (cudaHostGetDevicePointer(&din, b.in, 0) != cudaSuccess || cudaHostGetDevicePointer(&dout, b.out, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    memcpy(b.in, in, ib);
+    cudaError_t e = enqueue(c, kind, n, din, dout, (long long) batch, (long long) in_elems(kind, n),
+                            (long long) out_elems(kind, n), cudaStreamPerThread);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
+    if (e != cudaSuccess) { set_error("transform failed", e); return 0; }
+    memcpy(out, b.out, ob);
+    return 1;
+}
+
 // Host arrays: stream the batch through the GPU in chunks, three in flight
 // (H2D of chunk i+1, kernel of chunk i and D2H of chunk i-1 overlap on separate streams).
 int run_host(const _CkFftContext* c, Kind kind, int n, const void* in, void* out, size_t batch)
@@ -347,7 +394,10 @@ int run_sync(CkFftContext* c, Kind kind, int n, const void* in, void* out, size_
         set_error("input and output must both be host memory or both be memory of the context's device");
         return 0;
     }
-    if (si == SIDE_HOST) return run_host(c, kind, n, in, out, batch);
+    if (si == SIDE_HOST) {
+        const int small = run_host_small(c, kind, n, in, out, batch);
+        return small >= 0 ? small : run_host(c, kind, n, in, out, batch);
+    }
     if (((uintptr_t) in | (uintptr_t) out) & 7) { set_error("device pointers must be 8-byte aligned"); return 0; }
     cudaError_t e = enqueue(c, kind, n, in, out, (long long) batch, (long long) in_elems(kind, n),
                             (long long) out_elems(kind, n), cudaStreamPerThread);
