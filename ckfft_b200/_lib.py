@@ -17,7 +17,10 @@ B200_SYMBOLS = ["CkFftComplexForwardBatch", "CkFftComplexInverseBatch", "CkFftRe
                 "CkFftRealForwardBatchAsync", "CkFftRealInverseBatchAsync", "CkFftB200GetPlan",
                 "CkFftB200LastError", "CkFftB200KernelLaunches", "CkFftB200HostAlloc", "CkFftB200HostFree",
                 "CkFftB200ContextDevice", "CkFftB200PackColumnsAsync", "CkFftB200UnpackTransposeAsync",
-                "CkFftB200TwiddleRowsAsync", "CkFftB200RealForwardPowerBatchAsync"]
+                "CkFftB200TwiddleRowsAsync", "CkFftB200RealForwardPowerBatchAsync",
+                "CkFftB200DistGetLayout", "CkFftB200DistDescribe", "CkFftB200PeerAlloc", "CkFftB200PeerFree",
+                "CkFftB200PeerExport", "CkFftB200PeerOpen", "CkFftB200PeerClose", "CkFftB200DistPlanCreate",
+                "CkFftB200DistExecAsync", "CkFftB200DistPlanStatus", "CkFftB200DistPlanDestroy"]
 
 
 class Plan(C.Structure):
@@ -25,6 +28,20 @@ class Plan(C.Structure):
     _fields_ = [("n", C.c_int), ("isReal", C.c_int), ("complexPoints", C.c_int), ("passes", C.c_int),
                 ("radix", (C.c_int * 3) * 2), ("threadsPerTransform", C.c_int), ("elemsPerThread", C.c_int),
                 ("transformsPerCta", C.c_int), ("sharedBytes", C.c_int)]
+
+
+class DistLayout(C.Structure):
+    """CkFftB200DistLayout"""
+    _fields_ = [("log2n", C.c_int), ("world", C.c_int), ("log2n1", C.c_int), ("log2n2", C.c_int), ("la", C.c_int),
+                ("lb", C.c_int), ("lc", C.c_int), ("ld", C.c_int), ("passes", C.c_int)]
+
+
+class DistPass(C.Structure):
+    """CkFftB200DistPass"""
+    _fields_ = [("kind", C.c_int), ("routed", C.c_int), ("L", C.c_int), ("nproblems", C.c_longlong), ("ncols", C.c_int),
+                ("twLog2", C.c_int), ("twColBase", C.c_int), ("twColShift", C.c_int), ("kProbMul", C.c_int),
+                ("kMul", C.c_int), ("rankShift", C.c_int), ("outRowStride", C.c_longlong), ("outColBase", C.c_longlong),
+                ("inColStride", C.c_longlong), ("inProbStride", C.c_longlong), ("src", C.c_int), ("dst", C.c_int)]
 
 
 _lib = None
@@ -65,5 +82,22 @@ def load() -> C.CDLL:
     lib.CkFftB200UnpackTransposeAsync.argtypes = [vp, vp, i, sz, sz, vp]
     lib.CkFftB200TwiddleRowsAsync.argtypes = [vp, i, vp, sz, sz, sz, i, vp]
     lib.CkFftB200RealForwardPowerBatchAsync.argtypes = [vp, i, vp, vp, vp, sz, sz, sz, vp]
+    lib.CkFftB200DistGetLayout.argtypes = [C.c_longlong, i, i, C.POINTER(DistLayout)]
+    lib.CkFftB200DistDescribe.argtypes = [C.POINTER(DistLayout), i, C.POINTER(DistPass)]
+    lib.CkFftB200PeerAlloc.restype = vp
+    lib.CkFftB200PeerAlloc.argtypes = [sz]
+    lib.CkFftB200PeerFree.restype = None
+    lib.CkFftB200PeerFree.argtypes = [vp]
+    lib.CkFftB200PeerExport.argtypes = [vp, C.c_char_p]
+    lib.CkFftB200PeerOpen.restype = vp
+    lib.CkFftB200PeerOpen.argtypes = [C.c_char_p]
+    lib.CkFftB200PeerClose.restype = None
+    lib.CkFftB200PeerClose.argtypes = [vp]
+    lib.CkFftB200DistPlanCreate.restype = vp
+    lib.CkFftB200DistPlanCreate.argtypes = [vp, C.c_longlong, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.CkFftB200DistExecAsync.argtypes = [vp, vp, i, vp]
+    lib.CkFftB200DistPlanStatus.argtypes = [vp]
+    lib.CkFftB200DistPlanDestroy.restype = None
+    lib.CkFftB200DistPlanDestroy.argtypes = [vp]
     _lib = lib
     return lib

@@ -34,6 +34,7 @@ UNITS = [
     ("tiny.o", "tiny.cu", []),
     ("four_step.o", "four_step.cu", []),
     ("dist_glue.o", "dist_glue.cu", []),
+    ("dist_fused.o", "dist_fused.cu", []),
     ("c2c_fwd.o", "fft_variants.cu", ["-DCKB_VARIANT=0"]),
     ("c2c_inv.o", "fft_variants.cu", ["-DCKB_VARIANT=1"]),
     ("r2c.o", "fft_variants.cu", ["-DCKB_VARIANT=2"]),

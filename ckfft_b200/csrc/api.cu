@@ -784,4 +784,128 @@ int CkFftB200TwiddleRowsAsync(CkFftContext* c, int n, CkFftComplex* data, size_t
     return 1;
 }
 
+// ---- fused distributed transform (dist_fused.cu): layout, peer memory, plan ----
+int CkFftB200DistGetLayout(long long n, int world, int preferPasses, CkFftB200DistLayout* layout)
+{
+    if (!ckb::dist_layout(n, world, preferPasses, layout)) { set_error("distributed layout: n must be a power of two in 2^14..2^30 with whole 16-column tiles per rank"); return 0; }
+    return 1;
+}
+
+int CkFftB200DistDescribe(const CkFftB200DistLayout* layout, int rank, CkFftB200DistPass passes[4])
+{
+    if (!layout || !passes || rank < 0 || rank >= layout->world) return 0;
+    return ckb::dist_describe(*layout, rank, passes);
+}
+
+void* CkFftB200PeerAlloc(size_t bytes)
+{
+    void* p = NULL;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error("peer allocation", e); if (p) cudaFree(p); return NULL; }
+    return p;
+}
+
+void CkFftB200PeerFree(void* p) { if (p) cudaFree(p); }
+
+int CkFftB200PeerExport(void* p, unsigned char handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (!p || !handle) { set_error("peer export: NULL argument"); return 0; }
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { set_error("cudaIpcGetMemHandle", e); return 0; }
+    memcpy(handle, &h, 64);
+    return 1;
+}
+
+void* CkFftB200PeerOpen(const unsigned char handle[64])
+{
+    if (!handle) { set_error("peer open: NULL handle"); return NULL; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = NULL;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle", e); return NULL; }
+    return p;
+}
+
+void CkFftB200PeerClose(void* p) { if (p) cudaIpcCloseMemHandle(p); }
+
+struct CkFftB200DistPlan
+{
+    uint32_t magic;
+    CkFftContext* ctx;
+    CkFftB200DistLayout layout;
+    int rank;
+    ckb::DistBuffers bufs;
+    unsigned epoch;
+};
+
+CkFftB200DistPlan* CkFftB200DistPlanCreate(CkFftContext* c, long long n, int rank, int world, int preferPasses,
+                                           void* const* work, void* const* mid, void* const* out, void* const* flags)
+{
+    if (!c || c->magic != kMagic) { set_error("invalid context"); return NULL; }
+    if (!c->fwdExpTable && !c->invExpTable) { set_error("invalid context"); return NULL; }
+    if (n > c->maxCount || !c->dTwLo) { set_error("distributed plan: the context must be created with nMax >= n"); return NULL; }
+    CkFftB200DistLayout lay;
+    if (!CkFftB200DistGetLayout(n, world, preferPasses, &lay)) return NULL;
+    if (rank < 0 || rank >= world || !work || !mid || !out || !flags) { set_error("distributed plan: bad arguments"); return NULL; }
+    CkFftB200DistPlan* p = (CkFftB200DistPlan*) calloc(1, sizeof(CkFftB200DistPlan));
+    if (!p) { set_error("out of host memory"); return NULL; }
+    for (int q = 0; q < world; ++q) {
+        if (!work[q] || !mid[q] || !out[q] || !flags[q] || (((uintptr_t) work[q] | (uintptr_t) mid[q] | (uintptr_t) out[q]) & 127)) {
+            set_error("distributed plan: every rank's buffers must be non-NULL and 128-byte aligned");
+            free(p);
+            return NULL;
+        }
+        p->bufs.buf[0][q] = (ckb::cf*) work[q];
+        p->bufs.buf[1][q] = (ckb::cf*) mid[q];
+        p->bufs.buf[2][q] = (ckb::cf*) out[q];
+        p->bufs.flags[q] = (unsigned*) flags[q];
+    }
+    p->magic = kMagic;
+    p->ctx = c;
+    p->layout = lay;
+    p->rank = rank;
+    p->epoch = 0;
+    return p;
+}
+
+int CkFftB200DistExecAsync(CkFftB200DistPlan* p, const CkFftComplex* input, int inverse, void* stream)
+{
+    if (!p || p->magic != kMagic || !p->ctx || p->ctx->magic != kMagic) { set_error("invalid distributed plan"); return 0; }
+    const _CkFftContext* c = p->ctx;
+    if (inverse ? !c->invExpTable : !c->fwdExpTable) { set_error("context was not created for this direction"); return 0; }
+    if (!input || ((uintptr_t) input & 15)) { set_error("distributed exec: input must be a 16-byte aligned device pointer"); return 0; }
+    for (int k = 0; k < 3; ++k)
+        if ((const void*) input == (const void*) p->bufs.buf[k][p->rank]) { set_error("distributed exec: input must not be one of the plan's buffers"); return 0; }
+    DeviceGuard guard(c->device);
+    if (!guard.ok) { set_error("cannot select the context's device"); return 0; }
+    cudaError_t e = ckb::dist_exec(p->layout, p->rank, p->bufs, &p->epoch, (const ckb::cf*) input, inverse != 0, c->dTable,
+                                   c->log2Table, big_tw(c), (cudaStream_t) stream);
+    if (e != cudaSuccess) { set_error("distributed exec", e); return 0; }
+    return 1;
+}
+
+int CkFftB200DistPlanStatus(CkFftB200DistPlan* p)
+{
+    if (!p || p->magic != kMagic) { set_error("invalid distributed plan"); return 0; }
+    DeviceGuard guard(p->ctx->device);
+    unsigned err = 0;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(&err, p->bufs.flags[p->rank] + CKB_MAX_PEERS, sizeof(err), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error("distributed status", e); return 0; }
+    if (err) { set_error("distributed transform: a peer did not reach a barrier in time"); return 0; }
+    return 1;
+}
+
+void CkFftB200DistPlanDestroy(CkFftB200DistPlan* p)
+{
+    if (!p || p->magic != kMagic) return;
+    p->magic = 0;
+    free(p);
+}
+
 }  // extern "C"

@@ -26,6 +26,9 @@
 namespace ckb {
 
 enum TileKind { KIND_COLUMN = 0, KIND_LAST = 1 };
+#ifndef CKB_MAX_PEERS
+#define CKB_MAX_PEERS 8     /* GPUs of one NVSwitch domain a routed pass can store to */
+#endif
 
 struct TileParams {
     const cf* in;
@@ -41,6 +44,20 @@ struct TileParams {
     int P, Q;               // KIND_LAST: input column c starts at ((c % P) * Q + c / P) * L
     int stream_in;          // 1: the input is read once (ld.global.cs); 0: it was just written by the previous pass and
     int stream_out;         //    should be found in L2 (default policy).  Same for the output.
+    int tw_col_shift;       // column pass: the inter-pass twiddle is W_TN^(((tw_col_base + c) >> tw_col_shift) * k)
+    int tw_col_base;        //    (a column index that carries batch digits below the twiddle digits / a rank offset above them)
+    // ---- routed kernels (TileCfg::RT, the passes of the fused distributed transform, dist_fused.cu) ----
+    // Output bin k of column c of problem `prob` is row kk = prob * k_prob_mul + k * k_mul of a row-distributed
+    // [rows][out_row_stride] array: it goes to rank kk >> rank_shift, which may be a peer GPU (NVLink store), at
+    //     peer[kk >> rank_shift] + (kk & (2^rank_shift - 1)) * out_row_stride + out_col_base + c ,
+    // and the column pass multiplies it by W_TN^(((tw_col_base + c) >> tw_col_shift) * kk).
+    // Last pass: column c of problem `prob` is the contiguous run starting at in + c*in_col_stride + prob*in_prob_stride.
+    cf* peer[CKB_MAX_PEERS];
+    int k_prob_mul, k_mul;
+    int rank_shift;
+    long long out_row_stride;
+    long long out_col_base;
+    long long in_col_stride, in_prob_stride;
 };
 
 __device__ __forceinline__ cf ld_sel(const cf* p, int stream) { return stream ? __ldcs(p) : __ldg(p); }
@@ -51,9 +68,10 @@ __device__ __forceinline__ void st_sel(cf* p, cf v, int stream) { if (stream) __
 // the C contiguous columns with a 1-D cp.async.bulk.  The copy of the NEXT tile is issued as soon as the second
 // radix stage has gathered its inputs, i.e. it overlaps that stage's arithmetic, the inter-pass twiddles and the
 // stores; it lands in the same shared-memory buffer the exchange uses (no extra shared memory).
-template <int L_, int E_, int R0_, int R1_, int C_, bool INV_, int KIND_, int MINB_, bool PFT_ = false>
+template <int L_, int E_, int R0_, int R1_, int C_, bool INV_, int KIND_, int MINB_, bool PFT_ = false, bool RT_ = false>
 struct TileCfg {
     static constexpr bool PFT = PFT_;
+    static constexpr bool RT = RT_;     // routed: generalised output addressing (stores may target peer GPUs)
     static constexpr int L = L_, E = E_, R0 = R0_, R1 = R1_, C = C_, KIND = KIND_, MINB = MINB_;
     static constexpr bool INV = INV_;
     static constexpr int T = L / E;
@@ -128,6 +146,21 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
     const long long ntiles = p.nproblems * blocks_per_problem;
     const long long tn = (long long) L * p.ncols;
 
+    // start of (contiguous) input column c of a last-pass problem
+    auto last_src = [&](long long prob, int c) -> const cf* {
+        if constexpr (TC::RT) return p.in + (long long) c * p.in_col_stride + prob * p.in_prob_stride;
+        else return p.in + prob * tn + (long long) ((c % p.P) * p.Q + c / p.P) * L;
+    };
+    // where output bin k of column c of problem `prob` goes
+    auto out_ptr = [&](long long prob, int k, int c) -> cf* {
+        if constexpr (TC::RT) {
+            const long long kk = prob * p.k_prob_mul + (long long) k * p.k_mul;
+            return p.peer[kk >> p.rank_shift] + (kk & ((1LL << p.rank_shift) - 1)) * p.out_row_stride + p.out_col_base + c;
+        } else {
+            return p.out + prob * tn + c + (long long) k * p.ncols;
+        }
+    };
+
     // thread 0 asks the TMA unit for a whole tile: dense [L][C] (column pass) or [C][L] (last pass) in `xall`
     auto issue_tile = [&](long long t) {
         if (tid != 0 || t >= ntiles) return;
@@ -140,12 +173,8 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
             for (int r0 = 0; r0 < L; r0 += TC::BOX_ROWS)
                 tensor_load_2d(xall + r0 * C, &tmap_in, c0, (int) (prob * L + r0), mbar);
         } else {
-            const cf* pin = p.in + prob * tn;
 #pragma unroll
-            for (int g = 0; g < C; ++g) {
-                const int c = c0 + g;
-                bulk_load(xall + g * L, pin + (long long) ((c % p.P) * p.Q + c / p.P) * L, L * 8, mbar, l2pol);
-            }
+            for (int g = 0; g < C; ++g) bulk_load(xall + g * L, last_src(prob, c0 + g), L * 8, mbar, l2pol);
         }
     };
     unsigned phase = 0;
@@ -155,7 +184,6 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
         const long long prob = tile / blocks_per_problem;
         const int c0 = (int) (tile % blocks_per_problem) * C;
         const cf* __restrict__ pin = p.in + prob * tn;
-        cf* __restrict__ pout = p.out + prob * tn;
         cf v[E];
 
         if constexpr (TC::PFT) {
@@ -175,8 +203,7 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
         } else if constexpr (TC::KIND == KIND_COLUMN) {
             gather_rows<L, T, E, R0>(v, pin + c0 + g0, p.ncols, j0, p.stream_in);
         } else {
-            const int c = c0 + g0;
-            const cf* src = pin + (long long) ((c % p.P) * p.Q + c / p.P) * L;
+            const cf* src = last_src(prob, c0 + g0);
             if (p.stream_in) stage_gather<L, T, E, R0, LOGPAD, SRC_GLOBAL>(v, src, nullptr, j0, true);
             else             stage_gather<L, T, E, R0, LOGPAD, SRC_GLOBAL_KEEP>(v, src, nullptr, j0, true);
         }
@@ -192,32 +219,35 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
 
         // Results: this thread holds bins k = jq + u * (L / R1) of column c0 + g1, in natural u order.
         constexpr int B1 = E / R1, STR1 = L / R1;
-        cf* ocol = pout + c0 + g1;
+        const int ocol = c0 + g1;
         static_for<0, B1>([&](auto q_) {
             constexpr int q = decltype(q_)::value;
             const int jq = j1 + q * T;
             if constexpr (TC::KIND == KIND_COLUMN) {
                 // inter-pass twiddle W_TN^(cc * k), k = jq + u * STR1: geometric in u; with u = 4a + b it factors as
                 // A_a * B_b,  A_a = W^(cc * (jq + 4a*STR1)),  B_b = W^(cc * b*STR1): R1/4 + 3 table look-ups (two
-                // roundings deep) instead of R1.
-                const unsigned cc = (unsigned) (c0 + g1);
+                // roundings deep) instead of R1.  Routed passes: k -> kk = prob*k_prob_mul + k*k_mul (linear, so the
+                // same factorisation holds with B_b = W^(cc * k_mul*b*STR1)).
+                const unsigned cc = (unsigned) (p.tw_col_base + ocol) >> p.tw_col_shift;
+                const unsigned kmul = TC::RT ? (unsigned) p.k_mul : 1u;
+                const unsigned koff = TC::RT ? (unsigned) (prob * p.k_prob_mul) : 0u;
                 cf bb[3];
-                static_for<1, 4>([&](auto b_) { constexpr int b = decltype(b_)::value; bb[b - 1] = big_twiddle(p, cc, (unsigned) (b * STR1), INV); });
+                static_for<1, 4>([&](auto b_) { constexpr int b = decltype(b_)::value; bb[b - 1] = big_twiddle(p, cc, kmul * (unsigned) (b * STR1), INV); });
                 static_for<0, R1 / 4>([&](auto a_) {
                     constexpr int a = decltype(a_)::value;
-                    const cf aa = big_twiddle(p, cc, (unsigned) (jq + 4 * a * STR1), INV);
+                    const cf aa = big_twiddle(p, cc, koff + kmul * (unsigned) (jq + 4 * a * STR1), INV);
                     static_for<0, 4>([&](auto b_) {
                         constexpr int b = decltype(b_)::value;
                         constexpr int u = 4 * a + b;
                         cf val = cmul(v[q * R1 + u], aa);
                         if constexpr (b > 0) val = cmul(val, bb[b - 1]);
-                        st_sel(ocol + (long long) (jq + u * STR1) * p.ncols, val, p.stream_out);
+                        st_sel(out_ptr(prob, jq + u * STR1, ocol), val, p.stream_out);
                     });
                 });
             } else {
                 static_for<0, R1>([&](auto u_) {
                     constexpr int u = decltype(u_)::value;
-                    st_sel(ocol + (long long) (jq + u * STR1) * p.ncols, v[q * R1 + u], p.stream_out);
+                    st_sel(out_ptr(prob, jq + u * STR1, ocol), v[q * R1 + u], p.stream_out);
                 });
             }
         });
@@ -246,7 +276,7 @@ __device__ __forceinline__ cf glue_twiddle(const RealGlueParams& p, unsigned k)
 }
 
 // Z[0..M) -> Y[0..M]   (forward split)
-__global__ void __launch_bounds__(256) real_split_kernel(const RealGlueParams p)
+static __global__ void __launch_bounds__(256) real_split_kernel(const RealGlueParams p)
 {
     const long long per = p.M / 2 + 1;
     const long long total = p.batch * per;
@@ -271,7 +301,7 @@ __global__ void __launch_bounds__(256) real_split_kernel(const RealGlueParams p)
 }
 
 // Y[0..M] -> T[0..M)   (inverse twist)
-__global__ void __launch_bounds__(256) real_twist_kernel(const RealGlueParams p)
+static __global__ void __launch_bounds__(256) real_twist_kernel(const RealGlueParams p)
 {
     const long long per = p.M / 2 + 1;
     const long long total = p.batch * per;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "fft_kernel.cuh"
+#include "ckfft/ckfft_b200.h"
 
 namespace ckb {
 
@@ -37,6 +38,19 @@ cudaError_t launch_pack_columns(const cf* in, cf* out, long long rows, int parts
 cudaError_t launch_unpack_transpose(const cf* in, cf* out, int parts, long long rowsPer, long long w, cudaStream_t s);
 cudaError_t launch_twiddle_rows(cf* data, long long rows, long long cols, long long first_row, const BigTwiddles& tw,
                                 int log2n, bool inverse, cudaStream_t s);
+
+// fused distributed transform (dist_fused.cu)
+#ifndef CKB_MAX_PEERS
+#define CKB_MAX_PEERS 8
+#endif
+struct DistBuffers {
+    cf* buf[3][CKB_MAX_PEERS];          // [work, mid, out][rank]
+    unsigned* flags[CKB_MAX_PEERS];     // per rank: arrive[CKB_MAX_PEERS] + error word
+};
+bool dist_layout(long long n, int world, int prefer, CkFftB200DistLayout* out);
+int dist_describe(const CkFftB200DistLayout& l, int rank, CkFftB200DistPass passes[4]);
+cudaError_t dist_exec(const CkFftB200DistLayout& l, int rank, const DistBuffers& b, unsigned* epoch, const cf* in_local,
+                      bool inverse, const cf* table, int log2_nt, const BigTwiddles& tw, cudaStream_t s);
 
 struct PlanRow { int M, E, R0, R1, R2, G, MINB, smem_bytes; };
 const PlanRow* find_plan(int M);      // launch.cu: nullptr if M is not a single-pass length

@@ -123,6 +123,218 @@ class DistributedFFT:
         self.ctx.close()
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Fused variant: no collective library on the data path.  The transform passes store their results directly into
+# the memory of the GPU that needs them next (csrc/dist_fused.cu, include/ckfft/ckfft_b200.h "Fused distributed
+# transform"); torch.distributed only ships the 64-byte memory handles once, at set-up.
+# ---------------------------------------------------------------------------------------------------------------
+def fused_layout(n: int, world: int, prefer_passes: int = 0):
+    """CkFftB200DistGetLayout: how n = n1*n2 is factored into passes (pure host arithmetic, no GPU needed)."""
+    import ctypes as C
+
+    from . import _lib
+
+    lay = _lib.DistLayout()
+    if not _lib.load().CkFftB200DistGetLayout(int(n), int(world), int(prefer_passes), C.byref(lay)):
+        raise ValueError(f"n={n} cannot be spread over {world} ranks by the fused distributed transform")
+    return lay
+
+
+def fused_passes(layout, rank: int):
+    """CkFftB200DistDescribe: the pass descriptors of `rank` exactly as the library hands them to its kernels."""
+    from . import _lib
+
+    arr = (_lib.DistPass * 4)()
+    cnt = _lib.load().CkFftB200DistDescribe(layout, int(rank), arr)
+    return [arr[i] for i in range(cnt)]
+
+
+def replay_fused(slices, layout, inverse: bool = False, deliver=None, ranks=None):
+    """Replay the fused transform's exchange + pass descriptors in numpy (host-logic check of the routing algebra;
+    the arithmetic of a pass is numpy's FFT).  `slices[r]` is rank r's natural-order slice.  With `deliver=None` all
+    ranks are simulated in this process and the list of output slices is returned.  Otherwise only `ranks` are
+    simulated and every store goes through deliver(buffer_id, {dest_rank: (flat_indices, values)}, bufs), which moves
+    the data between processes (tests/test_distributed_cpu.py does that with gloo)."""
+    world = layout.world
+    n1, n2 = 1 << layout.log2n1, 1 << layout.log2n2
+    h, w = n1 // world, n2 // world
+    per = (n1 * n2) // world
+    ranks = list(range(world)) if ranks is None else list(ranks)
+    bufs = {r: [np.zeros(per, np.complex64) for _ in range(3)] for r in ranks}
+
+    def default_deliver(buf_id, outgoing, _bufs):
+        for q, (idx, val) in outgoing.items():
+            bufs[q][buf_id][idx] = val
+
+    deliver_fn = deliver or default_deliver
+    sign = 2.0 if inverse else -2.0
+
+    def fft(a, axis):
+        a = a.astype(np.complex128)
+        return (np.fft.ifft(a, axis=axis) * a.shape[axis] if inverse else np.fft.fft(a, axis=axis))
+
+    # exchange: rank s pushes the column blocks of its rows (exchange_push_kernel)
+    for r in ranks:
+        x = np.asarray(slices[r], np.complex64).reshape(h, n2)
+        rows = (r * h + np.arange(h))[:, None]
+        outgoing = {}
+        for q in range(world):
+            idx = rows * w + np.arange(w)[None, :]
+            outgoing[q] = (idx.reshape(-1), x[:, q * w:(q + 1) * w].reshape(-1))
+        deliver_fn(0, outgoing, bufs[r])
+    npass = len(fused_passes(layout, 0))
+    for i in range(npass):
+        staged = []
+        for r in ranks:
+            d = fused_passes(layout, r)[i]
+            src = bufs[r][d.src]
+            L, npr, nc = d.L, int(d.nproblems), d.ncols
+            k = np.arange(L, dtype=np.int64)
+            c = np.arange(nc, dtype=np.int64)
+            prob = np.arange(npr, dtype=np.int64)
+            kk = prob[:, None] * d.kProbMul + k[None, :] * d.kMul                     # [prob][k]
+            if d.kind == 0:
+                y = fft(src[:npr * L * nc].reshape(npr, L, nc), 1)
+                kt = kk if d.routed else np.broadcast_to(k[None, :], (npr, L))
+                cc = (d.twColBase + c) >> d.twColShift
+                tn = 1 << d.twLog2
+                e = (kt[:, :, None] * cc[None, None, :]) % tn
+                y = y * np.exp(1j * sign * np.pi * e / tn)
+            else:
+                assert d.routed
+                start = c[None, :] * d.inColStride + prob[:, None] * d.inProbStride  # [prob][c]
+                x = src[start[:, :, None] + k[None, None, :]]                        # [prob][c][k]
+                y = fft(x, 2).transpose(0, 2, 1)                                     # [prob][k][c]
+            y = y.astype(np.complex64)
+            if d.routed:
+                dest = kk >> d.rankShift
+                row = kk & ((1 << d.rankShift) - 1)
+                idx = row[:, :, None] * d.outRowStride + d.outColBase + c[None, None, :]
+                outgoing = {}
+                for q in range(world):
+                    m = np.broadcast_to((dest == q)[:, :, None], idx.shape)
+                    outgoing[q] = (idx[m], y[m])
+                staged.append((r, d.dst, outgoing))
+            else:
+                staged.append((r, d.dst, {r: (np.arange(npr * L * nc), y.reshape(-1))}))
+        for r, dst, outgoing in staged:      # all ranks finish the pass before anything lands (the flag barrier)
+            if list(outgoing.keys()) == [r]:
+                bufs[r][dst][outgoing[r][0]] = outgoing[r][1]
+            else:
+                deliver_fn(dst, outgoing, bufs[r])
+    return [bufs[r][2] for r in ranks]
+
+
+class _DeviceArray:
+    """Raw device memory as a CUDA-array-interface object (so torch can view a buffer the library allocated)."""
+
+    def __init__(self, ptr: int, nfloats: int):
+        self.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class FusedDistributedFFT:
+    """One N-point complex transform spread over the ranks of a process group, NVLink stores instead of collectives.
+
+    forward(x_local) / inverse(x_local): x_local is this rank's natural-order slice (complex64 CUDA tensor of
+    n/world elements); the result is a view of the plan's own output buffer, valid until the next call."""
+
+    def __init__(self, n: int, group=None, prefer_passes: int = 0):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+        from .api import BOTH, Context, CkFftError, last_error
+
+        self.torch, self.n, self.group = torch, n, group
+        self.lib = lib = _lib.load()
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.layout = fused_layout(n, self.world, prefer_passes)
+        self.ctx = Context(max(n, 1 << 15), BOTH)      # a multi-pass context: it carries the two-level twiddles of W_nMax
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        per_bytes = 8 * n // self.world
+        sizes = [per_bytes, per_bytes, per_bytes, 256]
+        self._own = []
+        for b in sizes:
+            ptr = lib.CkFftB200PeerAlloc(b)
+            if not ptr:
+                raise CkFftError("CkFftB200PeerAlloc: " + last_error())
+            self._own.append(ptr)
+        self._opened = []
+        table = [[None] * self.world for _ in sizes]      # [buffer][rank] -> device pointer valid in this process
+        if self.world > 1:
+            mine = []
+            for ptr in self._own:
+                h = C.create_string_buffer(64)
+                if not lib.CkFftB200PeerExport(ptr, h):
+                    raise CkFftError("CkFftB200PeerExport: " + last_error())
+                mine.append(h.raw)
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine, group=group)
+            for q in range(self.world):
+                for b in range(len(sizes)):
+                    if q == self.rank:
+                        table[b][q] = self._own[b]
+                    else:
+                        ptr = lib.CkFftB200PeerOpen(everyone[q][b])
+                        if not ptr:
+                            raise CkFftError(f"CkFftB200PeerOpen(rank {q}): " + last_error())
+                        self._opened.append(ptr)
+                        table[b][q] = ptr
+        else:
+            for b in range(len(sizes)):
+                table[b][0] = self._own[b]
+        arrs = [(C.c_void_p * self.world)(*table[b]) for b in range(len(sizes))]
+        self._plan = lib.CkFftB200DistPlanCreate(self.ctx.handle, n, self.rank, self.world, prefer_passes, *arrs)
+        if not self._plan:
+            raise CkFftError("CkFftB200DistPlanCreate: " + last_error())
+        flat = torch.as_tensor(_DeviceArray(self._own[2], 2 * n // self.world), device=self.device)
+        self.out = torch.view_as_complex(flat.view(-1, 2))
+        if self.world > 1:
+            dist.barrier(group=group)        # every rank has mapped everything before anyone starts storing
+
+    def _run(self, x_local, inverse):
+        from .api import CkFftError, last_error
+
+        x = x_local.reshape(-1)
+        assert x.is_cuda and x.dtype == self.torch.complex64 and x.numel() == self.n // self.world and x.is_contiguous()
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        if not self.lib.CkFftB200DistExecAsync(self._plan, x.data_ptr(), int(inverse), stream):
+            raise CkFftError("CkFftB200DistExecAsync: " + last_error())
+        return self.out
+
+    def forward(self, x_local):
+        return self._run(x_local, False)
+
+    def inverse(self, x_local):
+        return self._run(x_local, True)
+
+    def check(self):
+        """Synchronise and raise if a barrier of this plan ever timed out."""
+        from .api import CkFftError, last_error
+
+        if not self.lib.CkFftB200DistPlanStatus(self._plan):
+            raise CkFftError(last_error())
+
+    def bytes_per_exchange(self) -> int:
+        return (self.world - 1) * 8 * self.n // (self.world * self.world)
+
+    def close(self):
+        if getattr(self, "_plan", None):
+            self.torch.cuda.synchronize(self.device)
+            self.lib.CkFftB200DistPlanDestroy(self._plan)
+            self._plan = None
+            self.out = None
+            for p in self._opened:
+                self.lib.CkFftB200PeerClose(p)
+            for p in self._own:
+                self.lib.CkFftB200PeerFree(p)
+            self._opened, self._own = [], []
+            self.ctx.close()
+
+
 class NumpyBackend:
     """CPU stand-in used by the gloo tests: same slab arithmetic, numpy for the local steps.
     `fft_rows(a2d, inverse)` supplies the local transform (the tests pass the oracle)."""

@@ -103,6 +103,81 @@ int CkFftB200UnpackTransposeAsync(const CkFftComplex* in, CkFftComplex* out, int
 int CkFftB200TwiddleRowsAsync(CkFftContext* context, int n, CkFftComplex* data, size_t rows, size_t cols, size_t firstRow,
                               int inverse, void* stream);
 
+
+/*
+ * Fused distributed transform of ONE very large 1-D complex FFT over the P <= 8 GPUs of one NVSwitch domain
+ * (n = n1*n2 = 2^14 .. 2^30, one process per GPU, rank r owns the natural-order slice [r*n/P, (r+1)*n/P) of the
+ * input and of the output).  No collective library on the data path: the FFT passes themselves store their results
+ * into the memory of the GPU that needs them next (peer stores over NVLink, 128-byte row chunks), so each of
+ * the two inner all-to-all transposes of the six-step algorithm is fused into the transform pass that feeds it:
+ *
+ *   exchange  x[n1][n2], rows on rank(n1)            -> work[n1][n2 in my column block]          (push copy)
+ *   pass A    (n1 = a*lb + b, only if n1 > 1024)  la-point FFTs over a, * W_n1^(b*ka)             local
+ *   pass B    lb-point FFTs over b, * W_n^(n2*k1), row k1 stored on rank(k1): mid[k1][n2]         NVLink stores
+ *   pass C    (n2 = c*ld + d, only if n2 > 1024)  lc-point FFTs over c, * W_n2^(d*kc)             local
+ *   pass D    ld-point FFTs over d, X[k1 + n1*k2] stored on rank(k2): out[k2][k1]                 NVLink stores
+ *
+ * with a flag barrier over peer memory after the exchange, after pass B and after pass D.  The reference has no
+ * multi-device path; the index algebra is the six-step of ext/fftw-3.3.2/mpi/dft-rank1.c:58-79.
+ *
+ * Buffers: every rank allocates three arrays of n/P complex values (work, mid, out) and a 256-byte flag block with
+ * CkFftB200PeerAlloc, exports them (CkFftB200PeerExport, 64-byte handles the caller ships to the other processes by
+ * any means) and opens the peers' (CkFftB200PeerOpen).  The result of an execution is the rank's own `out` array; it
+ * stays valid until the next execution on the plan.  All ranks must execute the same sequence of calls.
+ */
+typedef struct
+{
+    int log2n, world;
+    int log2n1, log2n2;       /* n = n1 * n2 */
+    int la, lb;               /* n1 = la * lb (la = 1: n1 is one pass) */
+    int lc, ld;               /* n2 = lc * ld (lc = 1: n2 is one pass) */
+    int passes;               /* FFT passes over the data (2 .. 4), not counting the exchange */
+} CkFftB200DistLayout;
+
+/* One FFT pass as the tile kernel sees it (the CPU tests replay these descriptors in numpy). */
+typedef struct
+{
+    int kind;                 /* 0: column pass over a [L][ncols] array per problem, 1: last pass (contiguous columns) */
+    int routed;               /* 1: output rows are distributed over the ranks (see below), 0: local geometry */
+    int L;                    /* points per transform of this pass */
+    long long nproblems;
+    int ncols;
+    int twLog2;               /* kind 0: outputs are multiplied by W_(2^twLog2)^(cc * kt) */
+    int twColBase, twColShift;/*         cc = (twColBase + c) >> twColShift;  kt = k (local) or kk (routed) */
+    int kProbMul, kMul;       /* routed: bin k of problem q is row kk = q*kProbMul + k*kMul ...                */
+    int rankShift;            /*         ... of rank kk >> rankShift, local row kk & (2^rankShift - 1),        */
+    long long outRowStride;   /*         stored at row*outRowStride + outColBase + c of that rank's dst array  */
+    long long outColBase;
+    long long inColStride;    /* routed kind 1: column c of problem q starts at c*inColStride + q*inProbStride */
+    long long inProbStride;
+    int src, dst;             /* 0 work, 1 mid, 2 out */
+} CkFftB200DistPass;
+
+/* Pure host arithmetic (no GPU needed).  preferPasses: 0 = default, 3 or 4 forces that pass count where possible.
+ * Returns 1, or 0 if n is not a power of two in 2^14 .. 2^30 or cannot be spread over `world` ranks. */
+int CkFftB200DistGetLayout(long long n, int world, int preferPasses, CkFftB200DistLayout* layout);
+/* Fills passes[0 .. return value) for `rank`; at most 4. */
+int CkFftB200DistDescribe(const CkFftB200DistLayout* layout, int rank, CkFftB200DistPass passes[4]);
+
+/* Exportable device memory on the current device (zero-filled).  */
+void* CkFftB200PeerAlloc(size_t bytes);
+void CkFftB200PeerFree(void* p);
+int CkFftB200PeerExport(void* p, unsigned char handle[64]);
+void* CkFftB200PeerOpen(const unsigned char handle[64]);     /* in another process; maps the peer's allocation */
+void CkFftB200PeerClose(void* p);
+
+typedef struct CkFftB200DistPlan CkFftB200DistPlan;
+/* work/mid/out/flags: arrays of `world` device pointers, entry q = rank q's buffer (own allocation at q == rank).
+ * The context must have been created with nMax >= n (it carries the twiddles of W_n). */
+CkFftB200DistPlan* CkFftB200DistPlanCreate(CkFftContext* context, long long n, int rank, int world, int preferPasses,
+                                           void* const* work, void* const* mid, void* const* out, void* const* flags);
+/* Enqueue one transform of this rank's slice `input` (n/world complex, device memory, not one of the plan's
+ * buffers) on `stream`.  inverse != 0: un-normalised inverse.  Returns 1 if everything was enqueued. */
+int CkFftB200DistExecAsync(CkFftB200DistPlan* plan, const CkFftComplex* input, int inverse, void* stream);
+/* Synchronises the device and returns 1 if no barrier of this plan has timed out so far, else 0. */
+int CkFftB200DistPlanStatus(CkFftB200DistPlan* plan);
+void CkFftB200DistPlanDestroy(CkFftB200DistPlan* plan);
+
 #ifdef __cplusplus
 }
 #endif

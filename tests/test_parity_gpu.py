@@ -412,6 +412,74 @@ def test_six_step_glue_kernels():
 
 
 # ---------------------------------------------------------------------------------------------
+# fused distributed transform on one GPU (world = 1: the routed passes store into the GPU's own arrays, so the
+# exchange kernel, the flag barrier and every routed tile kernel run exactly as they do across NVLink)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("log2n", [14, 15, 17, 20, 21, 23, 24])
+def test_fused_distributed_single_rank(log2n):
+    from ckfft_b200.distributed import FusedDistributedFFT
+
+    n = 1 << log2n
+    rng = np.random.default_rng(log2n)
+    x = uniform_complex(rng, (n,))
+    want = oracle.fp64_c2c(x)
+    d = FusedDistributedFFT(n)
+    xd = torch.from_numpy(x).cuda()
+    y = d.forward(xd).clone()
+    assert rel_rms(y.cpu().numpy(), want) <= tolerance(n)
+    z = d.inverse(y)
+    assert rel_rms(z.cpu().numpy() / n, x) <= tolerance(n)
+    d.check()
+    d.close()
+
+
+@pytest.mark.parametrize("prefer", [3, 4])
+def test_fused_distributed_2_28_analytic(prefer):
+    """Four-pass and three-pass layouts at 2^28 points: closed-form spectrum of exponentials + an impulse."""
+    from ckfft_b200.distributed import FusedDistributedFFT
+
+    n = 1 << 28
+    d = FusedDistributedFFT(n, prefer_passes=prefer)
+    assert d.layout.passes == prefer
+    idx = torch.arange(n, device="cuda", dtype=torch.float64)
+    freqs, amps, n0 = [3, n // 3 + 1, n - 7], [1.0, 0.5, 0.25], 5
+    x = torch.zeros(n, dtype=torch.complex64, device="cuda")
+    for f, a in zip(freqs, amps):
+        ph = 2.0 * np.pi * ((idx * f) % n) / n
+        x += (a * torch.complex(torch.cos(ph), torch.sin(ph))).to(torch.complex64)
+    x[n0] += 1.0
+    y = d.forward(x)
+    ph = -2.0 * np.pi * ((idx * n0) % n) / n
+    want = torch.complex(torch.cos(ph), torch.sin(ph))
+    del ph, idx
+    for f, a in zip(freqs, amps):
+        want[f] += a * n
+    err = float(torch.linalg.vector_norm(y.to(torch.complex128) - want) / torch.linalg.vector_norm(want))
+    del want
+    assert err <= tolerance(n)
+    z = d.inverse(y.clone())
+    assert float(torch.linalg.vector_norm(z / n - x) / torch.linalg.vector_norm(x)) <= tolerance(n)
+    d.check()
+    d.close()
+    torch.cuda.empty_cache()
+
+
+def test_fused_distributed_rejects_bad_arguments():
+    from ckfft_b200.distributed import FusedDistributedFFT
+
+    lib = _lib.load()
+    d = FusedDistributedFFT(1 << 14)
+    x = torch.zeros(1 << 14, dtype=torch.complex64, device="cuda")
+    assert lib.CkFftB200DistExecAsync(d._plan, None, 0, None) == 0
+    assert lib.CkFftB200DistExecAsync(d._plan, d.out.data_ptr(), 0, None) == 0      # input aliases a plan buffer
+    assert lib.CkFftB200DistExecAsync(None, x.data_ptr(), 0, None) == 0
+    with ck.Context(1 << 12, ck.BOTH) as small:                                      # context too small for n
+        arr = (C.c_void_p * 1)(d._own[0])
+        assert not lib.CkFftB200DistPlanCreate(small.handle, 1 << 14, 0, 1, 0, arr, arr, arr, arr)
+    d.close()
+
+
+# ---------------------------------------------------------------------------------------------
 # audio front end (SURVEY 8f-4): window + real forward + power spectrum fused in one kernel
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [32, 64, 256, 1024, 2048, 4096, 8192, 32768])
