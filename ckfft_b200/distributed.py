@@ -105,7 +105,7 @@ class DistributedFFT:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         split_n(n, self.world)
-        self.ctx = Context(n, BOTH)          # nMax = n: two-level twiddles of W_n + tables for the local transforms
+        self.ctx = Context(max(n, 1 << 15), BOTH)   # a multi-pass context: two-level twiddles + tables for the local transforms
         self.backend = CudaBackend(self.ctx, group)
 
     def forward(self, x_local):
