@@ -20,7 +20,8 @@ B200_SYMBOLS = ["CkFftComplexForwardBatch", "CkFftComplexInverseBatch", "CkFftRe
                 "CkFftB200TwiddleRowsAsync", "CkFftB200RealForwardPowerBatchAsync",
                 "CkFftB200DistGetLayout", "CkFftB200DistDescribe", "CkFftB200PeerAlloc", "CkFftB200PeerFree",
                 "CkFftB200PeerExport", "CkFftB200PeerOpen", "CkFftB200PeerClose", "CkFftB200DistPlanCreate",
-                "CkFftB200DistExecAsync", "CkFftB200DistPlanStatus", "CkFftB200DistPlanDestroy"]
+                "CkFftB200DistExecAsync", "CkFftB200DistPlanStatus", "CkFftB200DistPlanDestroy",
+                "CkFftB200DistPlanSetProfiling", "CkFftB200DistPlanPhases"]
 
 
 class Plan(C.Structure):
@@ -97,6 +98,8 @@ def load() -> C.CDLL:
     lib.CkFftB200DistPlanCreate.argtypes = [vp, C.c_longlong, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.CkFftB200DistExecAsync.argtypes = [vp, vp, i, vp]
     lib.CkFftB200DistPlanStatus.argtypes = [vp]
+    lib.CkFftB200DistPlanSetProfiling.argtypes = [vp, i]
+    lib.CkFftB200DistPlanPhases.argtypes = [vp, C.POINTER(C.c_float), C.c_char_p, sz]
     lib.CkFftB200DistPlanDestroy.restype = None
     lib.CkFftB200DistPlanDestroy.argtypes = [vp]
     _lib = lib

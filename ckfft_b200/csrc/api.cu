@@ -841,6 +841,8 @@ struct CkFftB200DistPlan
     int rank;
     ckb::DistBuffers bufs;
     unsigned epoch;
+    bool profiling;
+    ckb::DistMarks marks;
 };
 
 CkFftB200DistPlan* CkFftB200DistPlanCreate(CkFftContext* c, long long n, int rank, int world, int preferPasses,
@@ -884,9 +886,42 @@ int CkFftB200DistExecAsync(CkFftB200DistPlan* p, const CkFftComplex* input, int 
     DeviceGuard guard(c->device);
     if (!guard.ok) { set_error("cannot select the context's device"); return 0; }
     cudaError_t e = ckb::dist_exec(p->layout, p->rank, p->bufs, &p->epoch, (const ckb::cf*) input, inverse != 0, c->dTable,
-                                   c->log2Table, big_tw(c), (cudaStream_t) stream);
+                                   c->log2Table, big_tw(c), (cudaStream_t) stream, p->profiling ? &p->marks : nullptr);
     if (e != cudaSuccess) { set_error("distributed exec", e); return 0; }
     return 1;
+}
+
+int CkFftB200DistPlanSetProfiling(CkFftB200DistPlan* p, int on)
+{
+    if (!p || p->magic != kMagic) { set_error("invalid distributed plan"); return 0; }
+    DeviceGuard guard(p->ctx->device);
+    if (on && !p->profiling) {
+        for (int i = 0; i < ckb::DistMarks::kMax; ++i)
+            if (cudaEventCreate(&p->marks.ev[i]) != cudaSuccess) { set_error("event creation"); return 0; }
+        p->marks.count = 0;
+        p->profiling = true;
+    } else if (!on && p->profiling) {
+        cudaDeviceSynchronize();
+        for (int i = 0; i < ckb::DistMarks::kMax; ++i) cudaEventDestroy(p->marks.ev[i]);
+        p->profiling = false;
+    }
+    return 1;
+}
+
+int CkFftB200DistPlanPhases(CkFftB200DistPlan* p, float* ms, char* names, size_t namesBytes)
+{
+    if (!p || p->magic != kMagic || !p->profiling || !ms || !names || namesBytes == 0) { set_error("phases: profiling is off or bad arguments"); return 0; }
+    DeviceGuard guard(p->ctx->device);
+    if (cudaDeviceSynchronize() != cudaSuccess) return 0;
+    names[0] = 0;
+    int n = 0;
+    for (int i = 1; i < p->marks.count; ++i) {
+        if (cudaEventElapsedTime(&ms[n], p->marks.ev[i - 1], p->marks.ev[i]) != cudaSuccess) { cudaGetLastError(); return 0; }
+        const size_t used = strlen(names);
+        snprintf(names + used, namesBytes - used, "%s%s", n ? "," : "", p->marks.name[i]);
+        ++n;
+    }
+    return n;
 }
 
 int CkFftB200DistPlanStatus(CkFftB200DistPlan* p)
@@ -904,6 +939,7 @@ int CkFftB200DistPlanStatus(CkFftB200DistPlan* p)
 void CkFftB200DistPlanDestroy(CkFftB200DistPlan* p)
 {
     if (!p || p->magic != kMagic) return;
+    CkFftB200DistPlanSetProfiling(p, 0);
     p->magic = 0;
     free(p);
 }

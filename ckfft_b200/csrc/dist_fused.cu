@@ -174,11 +174,18 @@ static cudaError_t launch_routed_pass(bool inverse, int kind, int L, const TileP
 }
 
 cudaError_t dist_exec(const CkFftB200DistLayout& l, int rank, const DistBuffers& b, unsigned* epoch, const cf* in_local,
-                      bool inverse, const cf* table, int log2_nt, const BigTwiddles& tw, cudaStream_t s)
+                      bool inverse, const cf* table, int log2_nt, const BigTwiddles& tw, cudaStream_t s, DistMarks* marks)
 {
     const long long n1 = 1LL << l.log2n1, n2 = 1LL << l.log2n2;
     const long long h = n1 / l.world, w = n2 / l.world;
     cudaError_t e;
+    if (marks) marks->count = 0;
+    auto mark = [&](const char* name) {
+        if (!marks || marks->count >= DistMarks::kMax) return;
+        cudaEventRecord(marks->ev[marks->count], s);
+        marks->name[marks->count++] = name;
+    };
+    mark("start");
     {
         PeerPtrs work{};
         for (int q = 0; q < l.world; ++q) work.p[q] = b.buf[0][q];
@@ -191,7 +198,9 @@ cudaError_t dist_exec(const CkFftB200DistLayout& l, int rank, const DistBuffers&
         count_launch();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
+    mark("exchange");
     if ((e = launch_barrier(b, rank, l.world, ++*epoch, s)) != cudaSuccess) return e;
+    mark("barrier");
 
     CkFftB200DistPass passes[4];
     const int np = dist_describe(l, rank, passes);
@@ -212,9 +221,12 @@ cudaError_t dist_exec(const CkFftB200DistLayout& l, int rank, const DistBuffers&
             p.out_row_stride = d.outRowStride; p.out_col_base = d.outColBase;
             p.in_col_stride = d.inColStride; p.in_prob_stride = d.inProbStride;
             e = launch_routed_pass(inverse, d.kind, d.L, p, s);
+            mark(d.kind == KIND_COLUMN ? "passB(push)" : "passD(push)");
             if (e == cudaSuccess) e = launch_barrier(b, rank, l.world, ++*epoch, s);
+            mark("barrier");
         } else {
             e = launch_local_pass(inverse, d.kind, d.L, p, s);
+            mark(d.src == 0 ? "passA" : "passC");
         }
         if (e != cudaSuccess) return e;
     }

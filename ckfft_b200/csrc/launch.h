@@ -49,8 +49,14 @@ struct DistBuffers {
 };
 bool dist_layout(long long n, int world, int prefer, CkFftB200DistLayout* out);
 int dist_describe(const CkFftB200DistLayout& l, int rank, CkFftB200DistPass passes[4]);
+struct DistMarks {                      // optional per-phase events of one execution (profiling)
+    static constexpr int kMax = 12;
+    cudaEvent_t ev[kMax];
+    const char* name[kMax];
+    int count;
+};
 cudaError_t dist_exec(const CkFftB200DistLayout& l, int rank, const DistBuffers& b, unsigned* epoch, const cf* in_local,
-                      bool inverse, const cf* table, int log2_nt, const BigTwiddles& tw, cudaStream_t s);
+                      bool inverse, const cf* table, int log2_nt, const BigTwiddles& tw, cudaStream_t s, DistMarks* marks);
 
 struct PlanRow { int M, E, R0, R1, R2, G, MINB, smem_bytes; };
 const PlanRow* find_plan(int M);      // launch.cu: nullptr if M is not a single-pass length

@@ -318,6 +318,18 @@ class FusedDistributedFFT:
         if not self.lib.CkFftB200DistPlanStatus(self._plan):
             raise CkFftError(last_error())
 
+    def profile(self, x_local, inverse: bool = False):
+        """One profiled execution: list of (phase name, device ms) as seen by this rank."""
+        import ctypes as C
+
+        self.lib.CkFftB200DistPlanSetProfiling(self._plan, 1)
+        self._run(x_local, inverse)
+        ms = (C.c_float * 12)()
+        names = C.create_string_buffer(512)
+        cnt = self.lib.CkFftB200DistPlanPhases(self._plan, ms, names, 512)
+        self.lib.CkFftB200DistPlanSetProfiling(self._plan, 0)
+        return list(zip(names.value.decode().split(","), [float(ms[i]) for i in range(cnt)]))
+
     def bytes_per_exchange(self) -> int:
         return (self.world - 1) * 8 * self.n // (self.world * self.world)
 

@@ -176,6 +176,11 @@ CkFftB200DistPlan* CkFftB200DistPlanCreate(CkFftContext* context, long long n, i
 int CkFftB200DistExecAsync(CkFftB200DistPlan* plan, const CkFftComplex* input, int inverse, void* stream);
 /* Synchronises the device and returns 1 if no barrier of this plan has timed out so far, else 0. */
 int CkFftB200DistPlanStatus(CkFftB200DistPlan* plan);
+/* Profiling: when on, every execution records an event after each of its kernels.  CkFftB200DistPlanPhases
+ * synchronises and returns the number of phases of the LAST execution, their device times in ms[] (room for 12)
+ * and their names, comma separated, in names[]. */
+int CkFftB200DistPlanSetProfiling(CkFftB200DistPlan* plan, int on);
+int CkFftB200DistPlanPhases(CkFftB200DistPlan* plan, float* ms, char* names, size_t namesBytes);
 void CkFftB200DistPlanDestroy(CkFftB200DistPlan* plan);
 
 #ifdef __cplusplus

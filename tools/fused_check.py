@@ -129,6 +129,10 @@ def main():
         ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
         if multi:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        phases = d.profile(noise)
+        sync()
+        if rank == 0:
+            print("   phases (rank 0, ms): " + "  ".join(f"{k} {v:.3f}" for k, v in phases), flush=True)
         if rank == 0:
             tol = 1e-6 * lg
             ms = float(ms.item())
