@@ -122,6 +122,16 @@ cudaError_t enqueue_large_c2c(const _CkFftContext* c, bool inv, int n, const ckb
 {
     if (!c->dTwLo) return cudaErrorNotSupported;
     if (in_stride != n || out_stride != n) return cudaErrorNotSupported;   // multi-pass path: dense batches only
+    if (n <= (1 << 20) && ckb::pipe_enabled() && (((uintptr_t) in) & 15) == 0) {
+        // two passes as one persistent kernel, intermediate ring resident in L2 (pipe_kernel.cuh)
+        const long long chunk = 1LL << 20;                 // problems per launch (keeps the ticket in 32 bits)
+        cudaError_t e = cudaSuccess;
+        for (long long done = 0; done < batch && e == cudaSuccess; done += chunk) {
+            const long long cnt = batch - done < chunk ? batch - done : chunk;
+            e = ckb::launch_pipe(inv, ilog2i(n), in + done * n, out + done * n, cnt, c->dTable, c->log2Table, big_tw(c), s);
+        }
+        return e;
+    }
     const size_t per = (size_t) n * sizeof(ckb::cf);
     long long sub = (long long) (l2_group_bytes() / per);
     if (sub < 1) sub = 1;

@@ -1,5 +1,6 @@
 // four_step.cu -- host planner and launchers of the multi-pass path (see four_step.cuh).
 #include "tile_launch.h"
+#include "pipe_kernel.cuh"
 #include "plans.h"
 
 namespace ckb {
@@ -59,6 +60,110 @@ cudaError_t launch_four_step(bool inverse, int log2n, const cf* in, cf* out, cf*
     p.in = scratch; p.out = out; p.nproblems = batch; p.ncols = L[0] * L[1]; p.P = L[0]; p.Q = L[1];
     p.stream_in = 0; p.stream_out = 1;
     return launch_local_pass(inverse, KIND_LAST, L[2], p, s);
+}
+
+// ---- two-pass lengths as one L2-resident dataflow kernel (pipe_kernel.cuh) --------------------------------
+// pipe plans: X(L0, L1, MINB) with the tile plans A = column pass over L0, B = last pass over L1 (256 threads each)
+template <int L, bool INV, int KIND> struct PipeTile;
+template <bool INV, int KIND> struct PipeTile<128, INV, KIND>  { using type = TileCfg<128, 16, 16, 8, 32, INV, KIND, 3, true>; };
+template <bool INV, int KIND> struct PipeTile<256, INV, KIND>  { using type = TileCfg<256, 16, 16, 16, 16, INV, KIND, 3, true>; };
+template <bool INV, int KIND> struct PipeTile<512, INV, KIND>  { using type = TileCfg<512, 32, 32, 16, 16, INV, KIND, 2, true>; };
+template <bool INV, int KIND> struct PipeTile<1024, INV, KIND> { using type = TileCfg<1024, 32, 32, 32, 8, INV, KIND, 2, true>; };
+
+#define CKB_PIPE_PLANS(X) \
+    X(128, 256, 4) \
+    X(256, 256, 4) \
+    X(256, 512, 2) \
+    X(512, 512, 2) \
+    X(512, 1024, 2) \
+    X(1024, 1024, 2)
+
+static long long env_ll(const char* name, long long dflt)
+{
+    const char* e = getenv(name);
+    return e && *e ? atoll(e) : dflt;
+}
+
+bool pipe_enabled()
+{
+    return env_ll("CKFFT_B200_PIPE", 1) != 0 && tensor_map_encoder() != nullptr;   // read per call: tests flip it
+}
+
+template <int L0, int L1, int MINB, bool INV>
+static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const cf* table, int log2_nt, const BigTwiddles& tw,
+                                   cudaStream_t s)
+{
+    using A = typename PipeTile<L0, INV, KIND_COLUMN>::type;
+    using B = typename PipeTile<L1, INV, KIND_LAST>::type;
+    using PC = PipeCfg<A, B, MINB>;
+    auto kern = pipe_kernel<PC, A, B>;
+    static int grid_cap[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (grid_cap[dev] == 0) {
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PC::SMEM_BYTES)) != cudaSuccess) return e;
+        int occ = 0;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PC::THREADS, PC::SMEM_BYTES)) != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        grid_cap[dev] = occ * sm_count_of_current_device();
+    }
+    constexpr long long N = (long long) L0 * L1;
+    constexpr int S = PC::T1 + PC::T2;
+    const long long items = batch * S;
+    if (items >= (1LL << 32) - (1 << 20) || batch * L0 >= (1LL << 32)) return cudaErrorInvalidValue;
+    const int grid = (int) (items < grid_cap[dev] ? items : grid_cap[dev]);
+
+    // pipeline depth: enough problems in flight that a pass-2 item never waits in steady state, ring twice that
+    long long lag = env_ll("CKFFT_B200_PIPE_LAG", (2LL * grid + S - 1) / S + 1);
+    long long ring = 2;
+    while (ring < 2 * lag) ring <<= 1;
+    const long long cap = env_ll("CKFFT_B200_PIPE_RING_MB", 64) << 20;
+    while (ring > 2 && ring * N * 8 > cap) ring >>= 1;
+    if (lag > ring / 2) lag = ring / 2;
+    if (lag > batch) lag = batch;
+    long long slots = ring;
+    while (slots / 2 >= batch && slots > 1) slots >>= 1;      // never more slots than problems
+
+    const size_t ring_bytes = (size_t) slots * N * sizeof(cf);
+    const size_t ctr_bytes = ((size_t) (2 * batch + 4) * sizeof(unsigned) + 127) & ~size_t(127);
+    unsigned char* ws = nullptr;
+    if ((e = cudaMallocAsync((void**) &ws, ring_bytes + ctr_bytes, s)) != cudaSuccess) return e;
+    unsigned* ctr = (unsigned*) (ws + ring_bytes);
+    if ((e = cudaMemsetAsync(ctr, 0, ctr_bytes, s)) != cudaSuccess) { cudaFreeAsync(ws, s); return e; }
+
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (!make_tile_map(&tmap, in, batch * L0, L1, A::BOX_ROWS, A::C)) { cudaFreeAsync(ws, s); return cudaErrorInvalidValue; }
+
+    PipeParams p{};
+    p.in = in; p.out = out; p.ring = (cf*) ws;
+    p.table = table; p.log2_nt = log2_nt;
+    p.tw_lo = tw.lo; p.tw_hi = tw.hi; p.tw_h = tw.h; p.tw_shift = tw.log2_tmax - ilog2(L0) - ilog2(L1);
+    p.batch = batch; p.ring_mask = (int) slots - 1; p.lag = (int) lag;
+    p.ticket = ctr; p.done1 = ctr + 4; p.done2 = ctr + 4 + batch;
+    kern<<<grid, PC::THREADS, PC::SMEM_BYTES, s>>>(p, tmap);
+    count_launch();
+    e = cudaGetLastError();
+    cudaError_t e2 = cudaFreeAsync(ws, s);
+    return e != cudaSuccess ? e : e2;
+}
+
+// `batch` dense transforms of 2^log2n points (2^15 .. 2^20), 16-byte aligned input
+cudaError_t launch_pipe(bool inverse, int log2n, const cf* in, cf* out, long long batch, const cf* table, int log2_nt,
+                        const BigTwiddles& tw, cudaStream_t s)
+{
+    int npass, L[3];
+    four_step_plan(log2n, &npass, L);
+    if (npass != 2 || ((uintptr_t) in & 15)) return cudaErrorNotSupported;
+#define X(L0_, L1_, MINB_) \
+    if (L[0] == L0_ && L[1] == L1_) \
+        return inverse ? launch_pipe_cfg<L0_, L1_, MINB_, true>(in, out, batch, table, log2_nt, tw, s) \
+                       : launch_pipe_cfg<L0_, L1_, MINB_, false>(in, out, batch, table, log2_nt, tw, s);
+    CKB_PIPE_PLANS(X)
+#undef X
+    return cudaErrorNotSupported;
 }
 
 static int glue_grid(long long items)

@@ -28,6 +28,9 @@ struct BigTwiddles { const cf* lo; const cf* hi; int h; int log2_tmax; };   // W
 void four_step_plan(int log2n, int* npass, int L[3]);
 cudaError_t launch_four_step(bool inverse, int log2n, const cf* in, cf* out, cf* scratch, long long batch,
                              const cf* table, int log2_nt, const BigTwiddles& tw, cudaStream_t s);
+bool pipe_enabled();                  // two-pass lengths as one L2-resident dataflow kernel (pipe_kernel.cuh)
+cudaError_t launch_pipe(bool inverse, int log2n, const cf* in, cf* out, long long batch, const cf* table, int log2_nt,
+                        const BigTwiddles& tw, cudaStream_t s);
 cudaError_t launch_real_split(const cf* z, cf* y, int n, long long batch, long long z_stride, long long y_stride,
                               const BigTwiddles& tw, cudaStream_t s);
 cudaError_t launch_real_twist(const cf* y, cf* t, int n, long long batch, long long y_stride, long long t_stride,

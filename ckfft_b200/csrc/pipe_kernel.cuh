@@ -1,0 +1,281 @@
+// pipe_kernel.cuh -- two-pass ("four-step") transforms of N = L0*L1 points (2^15 .. 2^20) as ONE persistent
+// dataflow kernel whose intermediate array never leaves the 126 MB L2.
+//
+// The two tile passes of four_step.cuh (column pass over [L0][L1] with the fused inter-pass twiddle, then the
+// contiguous last pass) each move the whole array through HBM: 2 reads + 2 writes per point, i.e. at most half the
+// copy roofline.  Here both passes are work items of one kernel:
+//   * items are handed out by a global ticket counter in a fixed order: the pass-1 tiles of problem i, then the
+//     pass-2 tiles of problem i - LAG.  A CTA only ever waits for items with smaller tickets, which are held by
+//     running CTAs, so the scheme cannot deadlock whatever subset of the grid is resident;
+//   * pass 1 writes its (twiddled) tile into a RING of a few problem slots instead of a full-size scratch array,
+//     pass 2 reads the slot back LAG problems later: the ring (<= 48 MiB) stays in L2, it is overwritten in place
+//     before its dirty lines are ever evicted, so HBM sees one read of the input and one write of the output;
+//   * dependencies are per-problem counters in global memory: done1[p] (pass-1 tiles stored; released with
+//     __threadfence + atomicAdd, acquired by the thread that issues the pass-2 bulk copies, followed by a
+//     generic->async proxy fence) and done2[p] (pass-2 tiles whose copies have landed in shared memory, which frees
+//     the ring slot for problem p + RING);
+//   * the loads stay TMA-staged and one item ahead: the ticket of the NEXT item is drawn and its tile requested
+//     as soon as the second radix stage has drained the buffer.
+// The arithmetic of a tile is exactly that of tile_kernel (same stage functions, same twiddle factorisation), so
+// results are bit-identical to the two-kernel path.
+#pragma once
+#include "four_step.cuh"
+
+namespace ckb {
+
+struct PipeParams {
+    const cf* in;
+    cf* out;
+    cf* ring;               // ring_slots problem slots of N complex values
+    const cf* table;
+    int log2_nt;
+    const cf* tw_lo;
+    const cf* tw_hi;
+    int tw_h;
+    int tw_shift;
+    long long batch;
+    int ring_mask;          // ring_slots - 1 (power of two)
+    int lag;                // pass-2 items of problem i - lag follow the pass-1 items of problem i (0 <= lag <= batch)
+    unsigned* ticket;
+    unsigned* done1;        // [batch]
+    unsigned* done2;        // [batch]
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long l2_evict_normal_policy()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+__device__ __forceinline__ void tensor_load_2d_hint(void* dst, const CUtensorMap* map, int x, int y, unsigned long long* bar,
+                                                    unsigned long long policy)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+__device__ __forceinline__ cf pipe_twiddle(const PipeParams& p, unsigned c, unsigned k, bool inverse)
+{
+    const unsigned e = (c * k) << p.tw_shift;              // c*k < N <= 2^20
+    cf w = cmul(__ldg(p.tw_lo + (e & ((1u << p.tw_h) - 1u))), __ldg(p.tw_hi + (e >> p.tw_h)));
+    if (inverse) w.y = -w.y;
+    return w;
+}
+
+// A: column-pass plan (L0, C0 columns of the [L0][L1] problem per tile), B: last-pass plan (L1, C1 contiguous columns)
+template <class A, class B, int MINB_>
+struct PipeCfg {
+    static_assert(A::THREADS == B::THREADS, "both passes run in the same CTA");
+    static_assert(A::INV == B::INV, "one direction");
+    static constexpr int THREADS = A::THREADS;
+    static constexpr int MINB = MINB_;
+    static constexpr int L0 = A::L, L1 = B::L;
+    static constexpr int T1 = L1 / A::C;          // pass-1 tiles per problem
+    static constexpr int T2 = L0 / B::C;          // pass-2 tiles per problem
+    static constexpr int XA = A::C * A::XBUF, XB = B::C * B::XBUF;
+    static constexpr int XALL = XA > XB ? XA : XB;
+    static constexpr int LUTA = A::LUT1, LUTB = B::LUT1;
+    static constexpr int SMEM_BYTES = 8 * (LUTA + LUTB + XALL) + 32;
+    static_assert(((LUTA + LUTB) * 8) % 128 == 0, "tile buffer alignment");
+};
+
+template <class PC, class A, class B>
+__global__ void __launch_bounds__(PC::THREADS, PC::MINB) pipe_kernel(const PipeParams p, const __grid_constant__ CUtensorMap tmap_in)
+{
+    constexpr int THREADS = PC::THREADS;
+    constexpr bool INV = A::INV;
+    constexpr int L0 = PC::L0, L1 = PC::L1;
+    constexpr int T1 = PC::T1, T2 = PC::T2, S = T1 + T2;
+    constexpr long long N = (long long) L0 * L1;
+
+    extern __shared__ __align__(128) unsigned char pipe_smem[];
+    cf* lutA = reinterpret_cast<cf*>(pipe_smem);
+    cf* lutB = lutA + PC::LUTA;
+    cf* xall = lutB + PC::LUTB;
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(xall + PC::XALL);
+    unsigned* next_slot = reinterpret_cast<unsigned*>(mbar + 1);
+    const int tid = threadIdx.x;
+
+    {
+        const int shA = p.log2_nt - ilog2(L0), shB = p.log2_nt - ilog2(L1);
+        for (int i = tid; i < PC::LUTA; i += THREADS) lutA[i] = table_w(p.table, ((i / A::R0 + 1) * (i % A::R0)) << shA, INV);
+        for (int i = tid; i < PC::LUTB; i += THREADS) lutB[i] = table_w(p.table, ((i / B::R0 + 1) * (i % B::R0)) << shB, INV);
+    }
+    if (tid == 0) mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned long long pol_stream = l2_evict_first_policy();
+    const unsigned long long pol_keep = l2_evict_normal_policy();
+
+    const long long lag = p.lag;
+    const unsigned long long head = (unsigned long long) lag * T1;                       // pass-1 only
+    const unsigned long long steady = (unsigned long long) (p.batch - lag) * S;          // alternating
+    const unsigned long long total = (unsigned long long) p.batch * S;
+
+    // ticket -> (pass, problem, first column)
+    auto decode = [&](unsigned long long t, int& pass, long long& prob, int& c0) {
+        if (t < head) { pass = 1; prob = (long long) (t / T1); c0 = (int) (t % T1) * A::C; return; }
+        t -= head;
+        if (t < steady) {
+            const long long step = (long long) (t / S);
+            const int r = (int) (t % S);
+            if (r < T1) { pass = 1; prob = lag + step; c0 = r * A::C; }
+            else        { pass = 2; prob = step; c0 = (r - T1) * B::C; }
+            return;
+        }
+        t -= steady;
+        pass = 2; prob = (p.batch - lag) + (long long) (t / T2); c0 = (int) (t % T2) * B::C;
+    };
+
+    // thread 0: check (block = false) or wait for (block = true) the item's dependencies, then ask the TMA unit for its
+    // tile.  A CTA must never block while it still holds an item whose completion it has not signalled -- the item it
+    // waits for could depend on that very item -- so the look-ahead issue only tries, and the blocking wait happens
+    // after the current item has been signalled.
+    auto issue = [&](unsigned long long t, bool block) -> bool {
+        int pass; long long prob; int c0;
+        decode(t, pass, prob, c0);
+        const unsigned* dep = nullptr;
+        unsigned need = 0;
+        if (pass == 1) {
+            if (prob > p.ring_mask) { dep = p.done2 + (prob - p.ring_mask - 1); need = T2; }   // slot read by problem prob - RING
+        } else {
+            dep = p.done1 + prob; need = T1;
+        }
+        if (dep) {
+            if (block) { while (ld_acquire_gpu(dep) < need) __nanosleep(64); }
+            else if (ld_acquire_gpu(dep) < need) return false;
+        }
+        if (pass == 1) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(mbar, L0 * A::C * 8);
+#pragma unroll
+            for (int r0 = 0; r0 < L0; r0 += A::BOX_ROWS)
+                tensor_load_2d_hint(xall + r0 * A::C, &tmap_in, c0, (int) (prob * L0 + r0), mbar, pol_stream);
+        } else {
+            asm volatile("fence.proxy.async;" ::: "memory");           // other CTAs' generic stores -> our async-proxy reads
+            mbar_expect_tx(mbar, L1 * B::C * 8);
+            const cf* slot = p.ring + (prob & p.ring_mask) * N;
+#pragma unroll
+            for (int g = 0; g < B::C; ++g) bulk_load(xall + g * L1, slot + (long long) (c0 + g) * L1, L1 * 8, mbar, pol_keep);
+        }
+        return true;
+    };
+
+    unsigned long long cur = 0;
+    if (tid == 0) {
+        cur = atomicAdd(p.ticket, 1u);
+        *next_slot = (unsigned) cur;
+        if (cur < total) issue(cur, true);
+    }
+    __syncthreads();
+    cur = *next_slot;
+    unsigned phase = 0;
+    bool pending = false;          // thread 0: the next item's tile has not been requested yet
+    unsigned long long nxt = 0;
+
+    while (cur < total) {
+        int pass; long long prob; int c0;
+        decode(cur, pass, prob, c0);
+        mbar_wait(mbar, phase);
+        phase ^= 1u;
+        if (pass == 1) {
+            constexpr int L = A::L, E = A::E, T = A::T, C = A::C, R0 = A::R0, R1 = A::R1, LOGPAD = A::LOGPAD, XBUF = A::XBUF;
+            const int g = tid % C, j = tid / C;               // along the columns, both stages
+            cf v[E];
+            constexpr int B0 = E / R0, STR0 = L / R0;
+            static_for<0, B0>([&](auto q_) {
+                constexpr int q = decltype(q_)::value;
+                static_for<0, R0>([&](auto t_) {
+                    constexpr int t = decltype(t_)::value;
+                    v[q * R0 + bitrev<R0>(t)] = xall[(j + q * T + t * STR0) * C + g];
+                });
+            });
+            __syncthreads();
+            stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j);
+            stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xall + g * XBUF, j, true);
+            __syncthreads();
+            stage_gather<L, T, E, R1, LOGPAD, SRC_XBUF>(v, nullptr, xall + g * XBUF, j, true);
+            __syncthreads();
+            if (tid == 0) {
+                nxt = atomicAdd(p.ticket, 1u);
+                *next_slot = (unsigned) nxt;
+                pending = nxt < total && !issue(nxt, false);
+            }
+            stage_math<T, E, R1, R0, INV, TW_LUT>(v, lutA, p.table, 0, j);
+            constexpr int B1 = E / R1, STR1 = L / R1;
+            const unsigned cc = (unsigned) (c0 + g);
+            cf* ocol = p.ring + (prob & p.ring_mask) * N + c0 + g;
+            static_for<0, B1>([&](auto q_) {
+                constexpr int q = decltype(q_)::value;
+                const int jq = j + q * T;
+                cf bb[3];
+                static_for<1, 4>([&](auto b_) { constexpr int b = decltype(b_)::value; bb[b - 1] = pipe_twiddle(p, cc, (unsigned) (b * STR1), INV); });
+                static_for<0, R1 / 4>([&](auto a_) {
+                    constexpr int a = decltype(a_)::value;
+                    const cf aa = pipe_twiddle(p, cc, (unsigned) (jq + 4 * a * STR1), INV);
+                    static_for<0, 4>([&](auto b_) {
+                        constexpr int b = decltype(b_)::value;
+                        constexpr int u = 4 * a + b;
+                        cf val = cmul(v[q * R1 + u], aa);
+                        if constexpr (b > 0) val = cmul(val, bb[b - 1]);
+                        ocol[(long long) (jq + u * STR1) * L1] = val;          // stays in L2 (default policy)
+                    });
+                });
+            });
+            __syncthreads();                                  // every thread's stores are issued ...
+            if (tid == 0) {
+                __threadfence();                              // ... and ordered before the counter at gpu scope
+                atomicAdd(p.done1 + prob, 1u);
+                if (pending) { issue(nxt, true); pending = false; }
+            }
+        } else {
+            constexpr int L = B::L, E = B::E, T = B::T, C = B::C, R0 = B::R0, R1 = B::R1, LOGPAD = B::LOGPAD, XBUF = B::XBUF;
+            const int g0 = tid / T, j0 = tid % T;             // stage 0 along the transform (contiguous columns)
+            const int g1 = tid % C, j1 = tid / C;             // stage 1 along the columns (row-chunk stores)
+            cf v[E];
+            constexpr int B0 = E / R0, STR0 = L / R0;
+            static_for<0, B0>([&](auto q_) {
+                constexpr int q = decltype(q_)::value;
+                static_for<0, R0>([&](auto t_) {
+                    constexpr int t = decltype(t_)::value;
+                    v[q * R0 + bitrev<R0>(t)] = xall[g0 * L + j0 + q * T + t * STR0];
+                });
+            });
+            __syncthreads();
+            if (tid == 0) atomicAdd(p.done2 + prob, 1u);      // the ring slot's data is in shared memory / registers
+            stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j0);
+            stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xall + g0 * XBUF, j0, true);
+            __syncthreads();
+            stage_gather<L, T, E, R1, LOGPAD, SRC_XBUF>(v, nullptr, xall + g1 * XBUF, j1, true);
+            __syncthreads();
+            if (tid == 0) {
+                nxt = atomicAdd(p.ticket, 1u);
+                *next_slot = (unsigned) nxt;
+                pending = nxt < total && !issue(nxt, false);
+            }
+            stage_math<T, E, R1, R0, INV, TW_LUT>(v, lutB, p.table, 0, j1);
+            constexpr int B1 = E / R1, STR1 = L / R1;
+            cf* ocol = p.out + prob * N + c0 + g1;
+            static_for<0, B1>([&](auto q_) {
+                constexpr int q = decltype(q_)::value;
+                const int jq = j1 + q * T;
+                static_for<0, R1>([&](auto u_) {
+                    constexpr int u = decltype(u_)::value;
+                    __stcs(ocol + (long long) (jq + u * STR1) * L0, v[q * R1 + u]);
+                });
+            });
+            if (tid == 0 && pending) { issue(nxt, true); pending = false; }   // this item was signalled above: safe to wait
+            __syncthreads();                                  // next_slot is visible to everyone
+        }
+        cur = *next_slot;
+    }
+}
+
+}  // namespace ckb

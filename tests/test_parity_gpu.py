@@ -108,6 +108,33 @@ def test_large_complex_vs_oracle(log2n):
     orc.close()
 
 
+@pytest.mark.parametrize("log2n,batch", [(15, 300), (16, 150), (17, 100), (18, 80), (19, 40), (20, 20)])
+def test_pipelined_two_pass_matches_two_kernel_path(log2n, batch):
+    """The L2-resident dataflow kernel (pipe_kernel.cuh) with enough problems to wrap its ring several times:
+    bit-identical to the two-kernel four-step path, and within tolerance of fp64 on a few transforms."""
+    import os
+
+    n = 1 << log2n
+    g = torch.Generator(device="cuda").manual_seed(log2n)
+    x = torch.view_as_complex(torch.empty((batch, n, 2), dtype=torch.float32, device="cuda").uniform_(-1, 1, generator=g))
+    with ck.Context(n, ck.BOTH) as ctx:
+        for inverse in (False, True):
+            f = ctx.complex_inverse if inverse else ctx.complex_forward
+            os.environ["CKFFT_B200_PIPE"] = "1"
+            try:
+                for rep in range(3):                     # repeated launches: counters and ring are per launch
+                    y = f(x)
+                torch.cuda.synchronize()
+                os.environ["CKFFT_B200_PIPE"] = "0"
+                y0 = f(x)
+                torch.cuda.synchronize()
+            finally:
+                os.environ.pop("CKFFT_B200_PIPE", None)
+            assert torch.equal(torch.view_as_real(y), torch.view_as_real(y0)), (n, inverse)
+            for b in (0, batch // 2, batch - 1):
+                assert rel_rms(y[b].cpu().numpy(), oracle.fp64_c2c(x[b].cpu().numpy(), inverse)) <= tolerance(n)
+
+
 @pytest.mark.parametrize("log2n", [16, 17, 20, 22])
 def test_large_real_vs_oracle(log2n):
     n = 1 << log2n
