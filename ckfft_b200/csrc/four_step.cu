@@ -71,8 +71,8 @@ template <bool INV, int KIND> struct PipeTile<512, INV, KIND>  { using type = Ti
 template <bool INV, int KIND> struct PipeTile<1024, INV, KIND> { using type = TileCfg<1024, 32, 32, 32, 8, INV, KIND, 2, true>; };
 
 #define CKB_PIPE_PLANS(X) \
-    X(128, 256, 4) \
-    X(256, 256, 4) \
+    X(128, 256, 3) \
+    X(256, 256, 3) \
     X(256, 512, 2) \
     X(512, 512, 2) \
     X(512, 1024, 2) \
@@ -95,7 +95,7 @@ static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const
 {
     using A = typename PipeTile<L0, INV, KIND_COLUMN>::type;
     using B = typename PipeTile<L1, INV, KIND_LAST>::type;
-    using PC = PipeCfg<A, B, MINB>;
+    using PC = PipeCfg<A, B, MINB, (L0 <= 256 && L1 <= 256)>;
     auto kern = pipe_kernel<PC, A, B>;
     static int grid_cap[64] = {0};
     int dev = 0;
@@ -105,7 +105,7 @@ static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const
     if (grid_cap[dev] == 0) {
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PC::SMEM_BYTES)) != cudaSuccess) return e;
         int occ = 0;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PC::THREADS, PC::SMEM_BYTES)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PC::THREADS + 64, PC::SMEM_BYTES)) != cudaSuccess) return e;
         if (occ < 1) return cudaErrorLaunchOutOfResources;
         grid_cap[dev] = occ * sm_count_of_current_device();
     }
@@ -143,7 +143,7 @@ static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const
     p.tw_lo = tw.lo; p.tw_hi = tw.hi; p.tw_h = tw.h; p.tw_shift = tw.log2_tmax - ilog2(L0) - ilog2(L1);
     p.batch = batch; p.ring_mask = (int) slots - 1; p.lag = (int) lag;
     p.ticket = ctr; p.done1 = ctr + 4; p.done2 = ctr + 4 + batch;
-    kern<<<grid, PC::THREADS, PC::SMEM_BYTES, s>>>(p, tmap);
+    kern<<<grid, PC::THREADS + 64, PC::SMEM_BYTES, s>>>(p, tmap);    // + the producer warp
     count_launch();
     e = cudaGetLastError();
     cudaError_t e2 = cudaFreeAsync(ws, s);

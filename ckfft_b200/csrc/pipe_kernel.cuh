@@ -14,8 +14,11 @@
 //     __threadfence + atomicAdd, acquired by the thread that issues the pass-2 bulk copies, followed by a
 //     generic->async proxy fence) and done2[p] (pass-2 tiles whose copies have landed in shared memory, which frees
 //     the ring slot for problem p + RING);
-//   * the loads stay TMA-staged and one item ahead: the ticket of the NEXT item is drawn and its tile requested
-//     as soon as the second radix stage has drained the buffer.
+//   * warp specialisation: 8 consumer warps do the arithmetic; a 9th (producer) warp draws the ticket of the NEXT
+//     item, polls its dependencies, requests its tile from the TMA unit as soon as the consumers have drained the
+//     buffer (mbarrier `free`), and raises the completion counter of the finished item once the consumers have issued
+//     their stores (mbarrier `stored`): no global round trip sits on the consumers' path, and they synchronise among
+//     themselves only twice per item (named barrier).
 // The arithmetic of a tile is exactly that of tile_kernel (same stage functions, same twiddle factorisation), so
 // results are bit-identical to the two-kernel path.
 #pragma once
@@ -71,8 +74,9 @@ __device__ __forceinline__ cf pipe_twiddle(const PipeParams& p, unsigned c, unsi
 }
 
 // A: column-pass plan (L0, C0 columns of the [L0][L1] problem per tile), B: last-pass plan (L1, C1 contiguous columns)
-template <class A, class B, int MINB_>
+template <class A, class B, int MINB_, bool SEP_ = false>
 struct PipeCfg {
+    static constexpr bool SEP = SEP_;             // the staged tile has a buffer of its own (next to the exchange buffer)
     static_assert(A::THREADS == B::THREADS, "both passes run in the same CTA");
     static_assert(A::INV == B::INV, "one direction");
     static constexpr int THREADS = A::THREADS;
@@ -83,14 +87,17 @@ struct PipeCfg {
     static constexpr int XA = A::C * A::XBUF, XB = B::C * B::XBUF;
     static constexpr int XALL = XA > XB ? XA : XB;
     static constexpr int LUTA = A::LUT1, LUTB = B::LUT1;
-    static constexpr int SMEM_BYTES = 8 * (LUTA + LUTB + XALL) + 32;
+    static constexpr int SA = A::C * A::L, SB = B::C * B::L;
+    static constexpr int STAGE = SEP_ ? (SA > SB ? SA : SB) : 0;
+    static constexpr int SMEM_BYTES = 8 * (LUTA + LUTB + XALL + STAGE) + 64;
+    static_assert((XALL * 8) % 128 == 0 || !SEP_, "staging buffer alignment");
     static_assert(((LUTA + LUTB) * 8) % 128 == 0, "tile buffer alignment");
 };
 
 template <class PC, class A, class B>
-__global__ void __launch_bounds__(PC::THREADS, PC::MINB) pipe_kernel(const PipeParams p, const __grid_constant__ CUtensorMap tmap_in)
+__global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const PipeParams p, const __grid_constant__ CUtensorMap tmap_in)
 {
-    constexpr int THREADS = PC::THREADS;
+    constexpr int THREADS = PC::THREADS;          // consumer threads; two more warps serve them (loader, signaller)
     constexpr bool INV = A::INV;
     constexpr int L0 = PC::L0, L1 = PC::L1;
     constexpr int T1 = PC::T1, T2 = PC::T2, S = T1 + T2;
@@ -100,19 +107,27 @@ __global__ void __launch_bounds__(PC::THREADS, PC::MINB) pipe_kernel(const PipeP
     cf* lutA = reinterpret_cast<cf*>(pipe_smem);
     cf* lutB = lutA + PC::LUTA;
     cf* xall = lutB + PC::LUTB;
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(xall + PC::XALL);
-    unsigned* next_slot = reinterpret_cast<unsigned*>(mbar + 1);
+    cf* stage = PC::SEP ? xall + PC::XALL : xall;      // where the TMA unit puts the tile
+    unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(xall + PC::XALL + PC::STAGE);   // tile landed (TMA complete_tx)
+    unsigned long long* bar_free = bar_full + 1;       // every consumer has drained the buffer (stage-1 gather done)
+    unsigned long long* bar_stored = bar_full + 2;     // every consumer has issued its global stores of the item
+    unsigned* item_slot = reinterpret_cast<unsigned*>(bar_full + 3);                         // [4]: ticket of item k at k & 3
     const int tid = threadIdx.x;
 
     {
         const int shA = p.log2_nt - ilog2(L0), shB = p.log2_nt - ilog2(L1);
-        for (int i = tid; i < PC::LUTA; i += THREADS) lutA[i] = table_w(p.table, ((i / A::R0 + 1) * (i % A::R0)) << shA, INV);
-        for (int i = tid; i < PC::LUTB; i += THREADS) lutB[i] = table_w(p.table, ((i / B::R0 + 1) * (i % B::R0)) << shB, INV);
+        for (int i = tid; i < PC::LUTA; i += THREADS + 64) lutA[i] = table_w(p.table, ((i / A::R0 + 1) * (i % A::R0)) << shA, INV);
+        for (int i = tid; i < PC::LUTB; i += THREADS + 64) lutB[i] = table_w(p.table, ((i / B::R0 + 1) * (i % B::R0)) << shB, INV);
     }
-    if (tid == 0) mbar_init(mbar, 1);
+    if (tid == 0) {
+        item_slot[4] = 0u;
+        item_slot[5] = 0xffffffffu;
+        mbar_init(bar_full, 1);
+        mbar_init(bar_free, THREADS);
+        mbar_init(bar_stored, THREADS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const unsigned long long pol_stream = l2_evict_first_policy();
-    const unsigned long long pol_keep = l2_evict_normal_policy();
+    __syncthreads();
 
     const long long lag = p.lag;
     const unsigned long long head = (unsigned long long) lag * T1;                       // pass-1 only
@@ -134,57 +149,90 @@ __global__ void __launch_bounds__(PC::THREADS, PC::MINB) pipe_kernel(const PipeP
         pass = 2; prob = (p.batch - lag) + (long long) (t / T2); c0 = (int) (t % T2) * B::C;
     };
 
-    // thread 0: check (block = false) or wait for (block = true) the item's dependencies, then ask the TMA unit for its
-    // tile.  A CTA must never block while it still holds an item whose completion it has not signalled -- the item it
-    // waits for could depend on that very item -- so the look-ahead issue only tries, and the blocking wait happens
-    // after the current item has been signalled.
-    auto issue = [&](unsigned long long t, bool block) -> bool {
-        int pass; long long prob; int c0;
-        decode(t, pass, prob, c0);
-        const unsigned* dep = nullptr;
-        unsigned need = 0;
-        if (pass == 1) {
-            if (prob > p.ring_mask) { dep = p.done2 + (prob - p.ring_mask - 1); need = T2; }   // slot read by problem prob - RING
-        } else {
-            dep = p.done1 + prob; need = T1;
+    if (tid >= THREADS) {
+        // ---------------- two service warps (one lane each): loader and signaller ----------------
+        // No global round trip (ticket atomic, dependency poll, the fence before a completion counter) sits on the
+        // consumers' critical path, and the two chains do not serialise each other: the loader draws the next ticket
+        // and polls its dependencies while the consumers work, then requests the tile the moment the buffer is free;
+        // the signaller raises done1 once the consumers have issued an item's stores.  Only the loader ever waits for
+        // other CTAs, and never for anything this CTA still has to signal (that is the signaller's job), so the
+        // ticket-order argument for deadlock freedom is unchanged.
+        volatile unsigned* sig_count = item_slot + 4;      // items whose completion the signaller has handled
+        volatile unsigned* last_item = item_slot + 5;      // index of the sentinel item once the loader has drawn it
+        if (tid == THREADS + 32) {
+            for (unsigned k = 0;; ++k) {                                   // signaller
+                while (!mbar_try_wait(bar_stored, k & 1u)) {
+                    if (k >= *last_item) return;                           // the consumers never run the sentinel
+                    __nanosleep(100);
+                }
+                int pass; long long prob; int c0;
+                decode(item_slot[k & 3u], pass, prob, c0);
+                if (pass == 1) {
+                    __threadfence();                                       // the consumers' stores, ordered at gpu scope before the counter
+                    atomicAdd(p.done1 + prob, 1u);
+                }
+                *sig_count = k + 1;
+            }
         }
-        if (dep) {
-            if (block) { while (ld_acquire_gpu(dep) < need) __nanosleep(64); }
-            else if (ld_acquire_gpu(dep) < need) return false;
-        }
-        if (pass == 1) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(mbar, L0 * A::C * 8);
+        if (tid != THREADS) return;
+        const unsigned long long pol_stream = l2_evict_first_policy();
+        const unsigned long long pol_keep = l2_evict_normal_policy();
+        auto wait_deps = [&](unsigned long long t) {
+            if (t >= total) return;
+            int pass; long long prob; int c0;
+            decode(t, pass, prob, c0);
+            if (pass == 1) {
+                if (prob > p.ring_mask)
+                    while (ld_acquire_gpu(p.done2 + (prob - p.ring_mask - 1)) < (unsigned) T2) __nanosleep(100);
+            } else {
+                while (ld_acquire_gpu(p.done1 + prob) < (unsigned) T1) __nanosleep(100);
+            }
+        };
+        auto request = [&](unsigned long long t, unsigned k) {        // item number k of this CTA carries ticket t
+            item_slot[k & 3u] = (unsigned) t;
+            if (t >= total) {                                          // sentinel: complete the phase without a copy
+                *last_item = k;
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_full)) : "memory");
+                return;
+            }
+            int pass; long long prob; int c0;
+            decode(t, pass, prob, c0);
+            if (pass == 1) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar_full, L0 * A::C * 8);
 #pragma unroll
-            for (int r0 = 0; r0 < L0; r0 += A::BOX_ROWS)
-                tensor_load_2d_hint(xall + r0 * A::C, &tmap_in, c0, (int) (prob * L0 + r0), mbar, pol_stream);
-        } else {
-            asm volatile("fence.proxy.async;" ::: "memory");           // other CTAs' generic stores -> our async-proxy reads
-            mbar_expect_tx(mbar, L1 * B::C * 8);
-            const cf* slot = p.ring + (prob & p.ring_mask) * N;
+                for (int r0 = 0; r0 < L0; r0 += A::BOX_ROWS)
+                    tensor_load_2d_hint(stage + r0 * A::C, &tmap_in, c0, (int) (prob * L0 + r0), bar_full, pol_stream);
+            } else {
+                asm volatile("fence.proxy.async;" ::: "memory");       // other CTAs' generic stores -> our async-proxy reads
+                mbar_expect_tx(bar_full, L1 * B::C * 8);
+                const cf* slot = p.ring + (prob & p.ring_mask) * N;
 #pragma unroll
-            for (int g = 0; g < B::C; ++g) bulk_load(xall + g * L1, slot + (long long) (c0 + g) * L1, L1 * 8, mbar, pol_keep);
+                for (int g = 0; g < B::C; ++g) bulk_load(stage + g * L1, slot + (long long) (c0 + g) * L1, L1 * 8, bar_full, pol_keep);
+            }
+        };
+        unsigned long long cur = atomicAdd(p.ticket, 1u);
+        wait_deps(cur);
+        request(cur, 0);
+        for (unsigned k = 0; cur < total; ++k) {
+            const unsigned long long nxt = atomicAdd(p.ticket, 1u);
+            wait_deps(nxt);
+            while (!mbar_try_wait(bar_free, k & 1u)) __nanosleep(40);
+            while (*sig_count < k) __nanosleep(40);                    // the signaller is never more than one item behind
+            request(nxt, k + 1);
+            cur = nxt;
         }
-        return true;
-    };
-
-    unsigned long long cur = 0;
-    if (tid == 0) {
-        cur = atomicAdd(p.ticket, 1u);
-        *next_slot = (unsigned) cur;
-        if (cur < total) issue(cur, true);
+        return;
     }
-    __syncthreads();
-    cur = *next_slot;
-    unsigned phase = 0;
-    bool pending = false;          // thread 0: the next item's tile has not been requested yet
-    unsigned long long nxt = 0;
 
-    while (cur < total) {
+    // ---------------- consumers: 256 threads, one named barrier between the radix stages ----------------
+    auto consumer_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); };
+    for (unsigned k = 0;; ++k) {
+        mbar_wait(bar_full, k & 1u);
+        const unsigned long long cur = item_slot[k & 3u];
+        if (cur >= total) break;
         int pass; long long prob; int c0;
         decode(cur, pass, prob, c0);
-        mbar_wait(mbar, phase);
-        phase ^= 1u;
         if (pass == 1) {
             constexpr int L = A::L, E = A::E, T = A::T, C = A::C, R0 = A::R0, R1 = A::R1, LOGPAD = A::LOGPAD, XBUF = A::XBUF;
             const int g = tid % C, j = tid / C;               // along the columns, both stages
@@ -194,20 +242,17 @@ __global__ void __launch_bounds__(PC::THREADS, PC::MINB) pipe_kernel(const PipeP
                 constexpr int q = decltype(q_)::value;
                 static_for<0, R0>([&](auto t_) {
                     constexpr int t = decltype(t_)::value;
-                    v[q * R0 + bitrev<R0>(t)] = xall[(j + q * T + t * STR0) * C + g];
+                    v[q * R0 + bitrev<R0>(t)] = stage[(j + q * T + t * STR0) * C + g];
                 });
             });
-            __syncthreads();
+            if constexpr (PC::SEP) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_free)) : "memory"); }    // staging buffer drained: the next tile may land
+            else consumer_sync();                             // the staged tile is consumed: the buffer now serves the exchange
             stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j);
             stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xall + g * XBUF, j, true);
-            __syncthreads();
+            consumer_sync();
             stage_gather<L, T, E, R1, LOGPAD, SRC_XBUF>(v, nullptr, xall + g * XBUF, j, true);
-            __syncthreads();
-            if (tid == 0) {
-                nxt = atomicAdd(p.ticket, 1u);
-                *next_slot = (unsigned) nxt;
-                pending = nxt < total && !issue(nxt, false);
-            }
+            if constexpr (PC::SEP) consumer_sync();           // the next item's scatter must not overtake this gather
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_free)) : "memory");
             stage_math<T, E, R1, R0, INV, TW_LUT>(v, lutA, p.table, 0, j);
             constexpr int B1 = E / R1, STR1 = L / R1;
             const unsigned cc = (unsigned) (c0 + g);
@@ -229,37 +274,28 @@ __global__ void __launch_bounds__(PC::THREADS, PC::MINB) pipe_kernel(const PipeP
                     });
                 });
             });
-            __syncthreads();                                  // every thread's stores are issued ...
-            if (tid == 0) {
-                __threadfence();                              // ... and ordered before the counter at gpu scope
-                atomicAdd(p.done1 + prob, 1u);
-                if (pending) { issue(nxt, true); pending = false; }
-            }
         } else {
             constexpr int L = B::L, E = B::E, T = B::T, C = B::C, R0 = B::R0, R1 = B::R1, LOGPAD = B::LOGPAD, XBUF = B::XBUF;
             const int g0 = tid / T, j0 = tid % T;             // stage 0 along the transform (contiguous columns)
             const int g1 = tid % C, j1 = tid / C;             // stage 1 along the columns (row-chunk stores)
+            if (tid == 0) atomicAdd(p.done2 + prob, 1u);      // the copies have landed: the ring slot is no longer needed
             cf v[E];
             constexpr int B0 = E / R0, STR0 = L / R0;
             static_for<0, B0>([&](auto q_) {
                 constexpr int q = decltype(q_)::value;
                 static_for<0, R0>([&](auto t_) {
                     constexpr int t = decltype(t_)::value;
-                    v[q * R0 + bitrev<R0>(t)] = xall[g0 * L + j0 + q * T + t * STR0];
+                    v[q * R0 + bitrev<R0>(t)] = stage[g0 * L + j0 + q * T + t * STR0];
                 });
             });
-            __syncthreads();
-            if (tid == 0) atomicAdd(p.done2 + prob, 1u);      // the ring slot's data is in shared memory / registers
+            if constexpr (PC::SEP) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_free)) : "memory"); }
+            else consumer_sync();
             stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j0);
             stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xall + g0 * XBUF, j0, true);
-            __syncthreads();
+            consumer_sync();
             stage_gather<L, T, E, R1, LOGPAD, SRC_XBUF>(v, nullptr, xall + g1 * XBUF, j1, true);
-            __syncthreads();
-            if (tid == 0) {
-                nxt = atomicAdd(p.ticket, 1u);
-                *next_slot = (unsigned) nxt;
-                pending = nxt < total && !issue(nxt, false);
-            }
+            if constexpr (PC::SEP) consumer_sync();
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_free)) : "memory");
             stage_math<T, E, R1, R0, INV, TW_LUT>(v, lutB, p.table, 0, j1);
             constexpr int B1 = E / R1, STR1 = L / R1;
             cf* ocol = p.out + prob * N + c0 + g1;
@@ -271,10 +307,8 @@ __global__ void __launch_bounds__(PC::THREADS, PC::MINB) pipe_kernel(const PipeP
                     __stcs(ocol + (long long) (jq + u * STR1) * L0, v[q * R1 + u]);
                 });
             });
-            if (tid == 0 && pending) { issue(nxt, true); pending = false; }   // this item was signalled above: safe to wait
-            __syncthreads();                                  // next_slot is visible to everyone
         }
-        cur = *next_slot;
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_stored)) : "memory");
     }
 }
 
