@@ -89,14 +89,15 @@ bool pipe_enabled()
     return env_ll("CKFFT_B200_PIPE", 1) != 0 && tensor_map_encoder() != nullptr;   // read per call: tests flip it
 }
 
-template <int L0, int L1, int MINB, bool INV>
+template <int L0, int L1, int MINB, bool INV, int NBUF>
 static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const cf* table, int log2_nt, const BigTwiddles& tw,
                                    cudaStream_t s)
 {
     using A = typename PipeTile<L0, INV, KIND_COLUMN>::type;
     using B = typename PipeTile<L1, INV, KIND_LAST>::type;
-    using PC = PipeCfg<A, B, MINB, (L0 <= 256 && L1 <= 256)>;
+    using PC = PipeCfg<A, B, MINB, NBUF>;
     auto kern = pipe_kernel<PC, A, B>;
+    constexpr int CTA = PC::THREADS + 64;                    // consumers + loader warp + signaller warp
     static int grid_cap[64] = {0};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -105,7 +106,7 @@ static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const
     if (grid_cap[dev] == 0) {
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PC::SMEM_BYTES)) != cudaSuccess) return e;
         int occ = 0;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PC::THREADS + 64, PC::SMEM_BYTES)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA, PC::SMEM_BYTES)) != cudaSuccess) return e;
         if (occ < 1) return cudaErrorLaunchOutOfResources;
         grid_cap[dev] = occ * sm_count_of_current_device();
     }
@@ -115,16 +116,19 @@ static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const
     if (items >= (1LL << 32) - (1 << 20) || batch * L0 >= (1LL << 32)) return cudaErrorInvalidValue;
     const int grid = (int) (items < grid_cap[dev] ? items : grid_cap[dev]);
 
-    // pipeline depth: enough problems in flight that a pass-2 item never waits in steady state, ring twice that
-    long long lag = env_ll("CKFFT_B200_PIPE_LAG", (2LL * grid + S - 1) / S + 1);
-    long long ring = 2;
-    while (ring < 2 * lag) ring <<= 1;
-    const long long cap = env_ll("CKFFT_B200_PIPE_RING_MB", 64) << 20;
-    while (ring > 2 && ring * N * 8 > cap) ring >>= 1;
-    if (lag > ring / 2) lag = ring / 2;
+    // Pipeline depth.  Every CTA holds up to 2 + NBUF tickets (computing, requested, drawn), so W = (2 + NBUF) * grid
+    // tickets are in flight; a pass-2 item finds its dependencies met without waiting if it trails its pass-1 items by
+    // at least W tickets (lag problems of S tickets), and a pass-1 item finds its ring slot drained if the ring is
+    // another W tickets longer.  The ring is capped so that it stays resident in L2.
+    const long long window = ((long long) (2 + NBUF) * grid + S - 1) / S;
+    long long lag = env_ll("CKFFT_B200_PIPE_LAG", window + 1);
+    long long slots = env_ll("CKFFT_B200_PIPE_RING", 2 * lag);
+    const long long cap = (env_ll("CKFFT_B200_PIPE_RING_MB", 64) << 20) / (N * 8);
+    if (slots > cap) slots = cap;
+    if (slots < 2) slots = 2;
+    if (lag > slots - 1) lag = slots - 1;
     if (lag > batch) lag = batch;
-    long long slots = ring;
-    while (slots / 2 >= batch && slots > 1) slots >>= 1;      // never more slots than problems
+    if (slots > batch) slots = batch;                        // never more slots than problems (then no slot is reused)
 
     const size_t ring_bytes = (size_t) slots * N * sizeof(cf);
     const size_t ctr_bytes = ((size_t) (2 * batch + 4) * sizeof(unsigned) + 127) & ~size_t(127);
@@ -141,9 +145,9 @@ static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const
     p.in = in; p.out = out; p.ring = (cf*) ws;
     p.table = table; p.log2_nt = log2_nt;
     p.tw_lo = tw.lo; p.tw_hi = tw.hi; p.tw_h = tw.h; p.tw_shift = tw.log2_tmax - ilog2(L0) - ilog2(L1);
-    p.batch = batch; p.ring_mask = (int) slots - 1; p.lag = (int) lag;
+    p.batch = batch; p.ring_slots = (int) slots; p.lag = (int) lag;
     p.ticket = ctr; p.done1 = ctr + 4; p.done2 = ctr + 4 + batch;
-    kern<<<grid, PC::THREADS + 64, PC::SMEM_BYTES, s>>>(p, tmap);    // + the producer warp
+    kern<<<grid, CTA, PC::SMEM_BYTES, s>>>(p, tmap);
     count_launch();
     e = cudaGetLastError();
     cudaError_t e2 = cudaFreeAsync(ws, s);
@@ -157,10 +161,15 @@ cudaError_t launch_pipe(bool inverse, int log2n, const cf* in, cf* out, long lon
     int npass, L[3];
     four_step_plan(log2n, &npass, L);
     if (npass != 2 || ((uintptr_t) in & 15)) return cudaErrorNotSupported;
+    const bool two = env_ll("CKFFT_B200_PIPE_NBUF", 1) == 2 && L[1] <= 256;     // ping-pong tile buffers (measurement knob)
 #define X(L0_, L1_, MINB_) \
-    if (L[0] == L0_ && L[1] == L1_) \
-        return inverse ? launch_pipe_cfg<L0_, L1_, MINB_, true>(in, out, batch, table, log2_nt, tw, s) \
-                       : launch_pipe_cfg<L0_, L1_, MINB_, false>(in, out, batch, table, log2_nt, tw, s);
+    if (L[0] == L0_ && L[1] == L1_) { \
+        if (two && L1_ <= 256) \
+            return inverse ? launch_pipe_cfg<L0_, L1_, MINB_, true, (L1_ <= 256 ? 2 : 1)>(in, out, batch, table, log2_nt, tw, s) \
+                           : launch_pipe_cfg<L0_, L1_, MINB_, false, (L1_ <= 256 ? 2 : 1)>(in, out, batch, table, log2_nt, tw, s); \
+        return inverse ? launch_pipe_cfg<L0_, L1_, MINB_, true, 1>(in, out, batch, table, log2_nt, tw, s) \
+                       : launch_pipe_cfg<L0_, L1_, MINB_, false, 1>(in, out, batch, table, log2_nt, tw, s); \
+    }
     CKB_PIPE_PLANS(X)
 #undef X
     return cudaErrorNotSupported;

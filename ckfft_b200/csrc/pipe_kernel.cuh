@@ -37,7 +37,7 @@ struct PipeParams {
     int tw_h;
     int tw_shift;
     long long batch;
-    int ring_mask;          // ring_slots - 1 (power of two)
+    int ring_slots;         // problem slots in the ring (> lag)
     int lag;                // pass-2 items of problem i - lag follow the pass-1 items of problem i (0 <= lag <= batch)
     unsigned* ticket;
     unsigned* done1;        // [batch]
@@ -74,9 +74,10 @@ __device__ __forceinline__ cf pipe_twiddle(const PipeParams& p, unsigned c, unsi
 }
 
 // A: column-pass plan (L0, C0 columns of the [L0][L1] problem per tile), B: last-pass plan (L1, C1 contiguous columns)
-template <class A, class B, int MINB_, bool SEP_ = false>
+template <class A, class B, int MINB_, int NBUF_ = 1>
 struct PipeCfg {
-    static constexpr bool SEP = SEP_;             // the staged tile has a buffer of its own (next to the exchange buffer)
+    static constexpr int NBUF = NBUF_;            // tile buffers (each is staging area, then exchange buffer, of one item)
+    static_assert(NBUF_ == 1 || NBUF_ == 2, "one buffer, or two in ping-pong");
     static_assert(A::THREADS == B::THREADS, "both passes run in the same CTA");
     static_assert(A::INV == B::INV, "one direction");
     static constexpr int THREADS = A::THREADS;
@@ -85,12 +86,10 @@ struct PipeCfg {
     static constexpr int T1 = L1 / A::C;          // pass-1 tiles per problem
     static constexpr int T2 = L0 / B::C;          // pass-2 tiles per problem
     static constexpr int XA = A::C * A::XBUF, XB = B::C * B::XBUF;
-    static constexpr int XALL = XA > XB ? XA : XB;
+    static constexpr int XALL = ((XA > XB ? XA : XB) + 15) & ~15;   // whole 128-byte lines
     static constexpr int LUTA = A::LUT1, LUTB = B::LUT1;
-    static constexpr int SA = A::C * A::L, SB = B::C * B::L;
-    static constexpr int STAGE = SEP_ ? (SA > SB ? SA : SB) : 0;
-    static constexpr int SMEM_BYTES = 8 * (LUTA + LUTB + XALL + STAGE) + 64;
-    static_assert((XALL * 8) % 128 == 0 || !SEP_, "staging buffer alignment");
+    static constexpr int SMEM_BYTES = 8 * (LUTA + LUTB + NBUF * XALL) + 64;
+    static_assert((XALL * 8) % 128 == 0, "tile buffer alignment");
     static_assert(((LUTA + LUTB) * 8) % 128 == 0, "tile buffer alignment");
 };
 
@@ -107,11 +106,11 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
     cf* lutA = reinterpret_cast<cf*>(pipe_smem);
     cf* lutB = lutA + PC::LUTA;
     cf* xall = lutB + PC::LUTB;
-    cf* stage = PC::SEP ? xall + PC::XALL : xall;      // where the TMA unit puts the tile
-    unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(xall + PC::XALL + PC::STAGE);   // tile landed (TMA complete_tx)
-    unsigned long long* bar_free = bar_full + 1;       // every consumer has drained the buffer (stage-1 gather done)
-    unsigned long long* bar_stored = bar_full + 2;     // every consumer has issued its global stores of the item
-    unsigned* item_slot = reinterpret_cast<unsigned*>(bar_full + 3);                         // [4]: ticket of item k at k & 3
+    constexpr int NBUF = PC::NBUF;
+    unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(xall + NBUF * PC::XALL);   // [2] tile landed (TMA complete_tx)
+    unsigned long long* bar_free = bar_full + 2;       // [2] every consumer has drained the buffer (stage-1 gather done)
+    unsigned long long* bar_stored = bar_full + 4;     // every consumer has issued its global stores of the item
+    unsigned* item_slot = reinterpret_cast<unsigned*>(bar_full + 5);                         // [4]: ticket of item k at k & 3
     const int tid = threadIdx.x;
 
     {
@@ -123,7 +122,9 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
         item_slot[4] = 0u;
         item_slot[5] = 0xffffffffu;
         mbar_init(bar_full, 1);
+        mbar_init(bar_full + 1, 1);
         mbar_init(bar_free, THREADS);
+        mbar_init(bar_free + 1, THREADS);
         mbar_init(bar_stored, THREADS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -182,53 +183,60 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
             int pass; long long prob; int c0;
             decode(t, pass, prob, c0);
             if (pass == 1) {
-                if (prob > p.ring_mask)
-                    while (ld_acquire_gpu(p.done2 + (prob - p.ring_mask - 1)) < (unsigned) T2) __nanosleep(100);
+                if (prob >= p.ring_slots)
+                    while (ld_acquire_gpu(p.done2 + (prob - p.ring_slots)) < (unsigned) T2) __nanosleep(100);
             } else {
                 while (ld_acquire_gpu(p.done1 + prob) < (unsigned) T1) __nanosleep(100);
             }
         };
         auto request = [&](unsigned long long t, unsigned k) {        // item number k of this CTA carries ticket t
             item_slot[k & 3u] = (unsigned) t;
+            const unsigned b = k % NBUF;
+            cf* stage = xall + b * PC::XALL;
+            unsigned long long* full = bar_full + b;
             if (t >= total) {                                          // sentinel: complete the phase without a copy
                 *last_item = k;
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_full)) : "memory");
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(full)) : "memory");
                 return;
             }
             int pass; long long prob; int c0;
             decode(t, pass, prob, c0);
             if (pass == 1) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(bar_full, L0 * A::C * 8);
+                mbar_expect_tx(full, L0 * A::C * 8);
 #pragma unroll
                 for (int r0 = 0; r0 < L0; r0 += A::BOX_ROWS)
-                    tensor_load_2d_hint(stage + r0 * A::C, &tmap_in, c0, (int) (prob * L0 + r0), bar_full, pol_stream);
+                    tensor_load_2d_hint(stage + r0 * A::C, &tmap_in, c0, (int) (prob * L0 + r0), full, pol_stream);
             } else {
                 asm volatile("fence.proxy.async;" ::: "memory");       // other CTAs' generic stores -> our async-proxy reads
-                mbar_expect_tx(bar_full, L1 * B::C * 8);
-                const cf* slot = p.ring + (prob & p.ring_mask) * N;
+                mbar_expect_tx(full, L1 * B::C * 8);
+                const cf* slot = p.ring + (prob % p.ring_slots) * N;
 #pragma unroll
-                for (int g = 0; g < B::C; ++g) bulk_load(stage + g * L1, slot + (long long) (c0 + g) * L1, L1 * 8, bar_full, pol_keep);
+                for (int g = 0; g < B::C; ++g) bulk_load(stage + g * L1, slot + (long long) (c0 + g) * L1, L1 * 8, full, pol_keep);
             }
         };
-        unsigned long long cur = atomicAdd(p.ticket, 1u);
-        wait_deps(cur);
-        request(cur, 0);
-        for (unsigned k = 0; cur < total; ++k) {
-            const unsigned long long nxt = atomicAdd(p.ticket, 1u);
-            wait_deps(nxt);
-            while (!mbar_try_wait(bar_free, k & 1u)) __nanosleep(40);
-            while (*sig_count < k) __nanosleep(40);                    // the signaller is never more than one item behind
-            request(nxt, k + 1);
-            cur = nxt;
+        // item j goes into buffer j % NBUF, which item j - NBUF must have drained; the signaller is kept within one item
+        // (sig_count >= j - 1 before request j), which bounds the phase distance on `stored` and the reuse of item_slot
+        for (unsigned j = 0;; ++j) {
+            const unsigned long long t = atomicAdd(p.ticket, 1u);
+            wait_deps(t);
+            if (j >= (unsigned) NBUF) {
+                const unsigned use = j / NBUF - 1;                                 // completion number of that buffer's barrier
+                while (!mbar_try_wait(bar_free + j % NBUF, use & 1u)) __nanosleep(40);
+            }
+            if (j >= 2) while (*sig_count + 1 < j) __nanosleep(40);
+            request(t, j);
+            if (t >= total) return;
         }
-        return;
     }
 
     // ---------------- consumers: 256 threads, one named barrier between the radix stages ----------------
     auto consumer_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); };
     for (unsigned k = 0;; ++k) {
-        mbar_wait(bar_full, k & 1u);
+        const unsigned b = k % NBUF;
+        cf* xb = xall + b * PC::XALL;                           // this item's buffer: staged tile first, exchange buffer after
+        unsigned long long* bfree = bar_free + b;
+        mbar_wait(bar_full + b, (k / NBUF) & 1u);
         const unsigned long long cur = item_slot[k & 3u];
         if (cur >= total) break;
         int pass; long long prob; int c0;
@@ -242,21 +250,19 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
                 constexpr int q = decltype(q_)::value;
                 static_for<0, R0>([&](auto t_) {
                     constexpr int t = decltype(t_)::value;
-                    v[q * R0 + bitrev<R0>(t)] = stage[(j + q * T + t * STR0) * C + g];
+                    v[q * R0 + bitrev<R0>(t)] = xb[(j + q * T + t * STR0) * C + g];
                 });
             });
-            if constexpr (PC::SEP) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_free)) : "memory"); }    // staging buffer drained: the next tile may land
-            else consumer_sync();                             // the staged tile is consumed: the buffer now serves the exchange
+            consumer_sync();                                  // the staged tile is consumed: the buffer now serves the exchange
             stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j);
-            stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xall + g * XBUF, j, true);
+            stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xb + g * XBUF, j, true);
             consumer_sync();
-            stage_gather<L, T, E, R1, LOGPAD, SRC_XBUF>(v, nullptr, xall + g * XBUF, j, true);
-            if constexpr (PC::SEP) consumer_sync();           // the next item's scatter must not overtake this gather
-            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_free)) : "memory");
+            stage_gather<L, T, E, R1, LOGPAD, SRC_XBUF>(v, nullptr, xb + g * XBUF, j, true);
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bfree)) : "memory");
             stage_math<T, E, R1, R0, INV, TW_LUT>(v, lutA, p.table, 0, j);
             constexpr int B1 = E / R1, STR1 = L / R1;
             const unsigned cc = (unsigned) (c0 + g);
-            cf* ocol = p.ring + (prob & p.ring_mask) * N + c0 + g;
+            cf* ocol = p.ring + (prob % p.ring_slots) * N + c0 + g;
             static_for<0, B1>([&](auto q_) {
                 constexpr int q = decltype(q_)::value;
                 const int jq = j + q * T;
@@ -285,17 +291,15 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
                 constexpr int q = decltype(q_)::value;
                 static_for<0, R0>([&](auto t_) {
                     constexpr int t = decltype(t_)::value;
-                    v[q * R0 + bitrev<R0>(t)] = stage[g0 * L + j0 + q * T + t * STR0];
+                    v[q * R0 + bitrev<R0>(t)] = xb[g0 * L + j0 + q * T + t * STR0];
                 });
             });
-            if constexpr (PC::SEP) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_free)) : "memory"); }
-            else consumer_sync();
-            stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j0);
-            stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xall + g0 * XBUF, j0, true);
             consumer_sync();
-            stage_gather<L, T, E, R1, LOGPAD, SRC_XBUF>(v, nullptr, xall + g1 * XBUF, j1, true);
-            if constexpr (PC::SEP) consumer_sync();
-            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_free)) : "memory");
+            stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j0);
+            stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xb + g0 * XBUF, j0, true);
+            consumer_sync();
+            stage_gather<L, T, E, R1, LOGPAD, SRC_XBUF>(v, nullptr, xb + g1 * XBUF, j1, true);
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bfree)) : "memory");
             stage_math<T, E, R1, R0, INV, TW_LUT>(v, lutB, p.table, 0, j1);
             constexpr int B1 = E / R1, STR1 = L / R1;
             cf* ocol = p.out + prob * N + c0 + g1;
