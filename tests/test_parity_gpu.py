@@ -526,3 +526,59 @@ def test_power_spectrum_vs_oracle(ctx_big, orc_big, n):
             assert got.shape == (batch, n // 2 + 1)
             # power = |Y|^2: relative error doubles; measured against the spectrum's total power
             assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 4 * tolerance(n), (n, batch)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused distributed transform, world = 2: two PROCESSES (CUDA IPC handles, flag barriers over mapped peer memory,
+# every routed store crossing a process boundary).  On a one-GPU box both ranks share the device -- the driver
+# time-slices their kernels, so a barrier costs a few time slices instead of microseconds, which is fine for a test.
+# ---------------------------------------------------------------------------------------------
+def _fused_two_rank_worker(rank, world, port, tmpdir, ndev):
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+
+    from ckfft_b200.distributed import FusedDistributedFFT
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank % ndev)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    for log2n in (14, 21):
+        n = 1 << log2n
+        rng = np.random.default_rng(100 + log2n)
+        x = uniform_complex(rng, (n,))                                   # same on every rank
+        per = n // world
+        d = FusedDistributedFFT(n)
+        xd = torch.from_numpy(x[rank * per:(rank + 1) * per]).cuda()
+        y = d.forward(xd).clone()
+        z = d.inverse(y).clone()
+        d.check()
+        parts, back = [None] * world, [None] * world
+        dist.all_gather_object(parts, y.cpu().numpy())
+        dist.all_gather_object(back, z.cpu().numpy())
+        if rank == 0:
+            want = np.fft.fft(x.astype(np.complex128))
+            ok = ok and rel_rms(np.concatenate(parts), want) <= tolerance(n)
+            ok = ok and rel_rms(np.concatenate(back) / n, x) <= tolerance(n)
+        dist.barrier()
+        d.close()
+    if rank == 0:
+        open(os.path.join(tmpdir, "ok"), "w").write("1" if ok else "0")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fused_distributed_two_processes(tmp_path):
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_fused_two_rank_worker, args=(2, port, str(tmp_path), torch.cuda.device_count()), nprocs=2, join=True)
+    assert (tmp_path / "ok").read_text() == "1"
