@@ -329,6 +329,9 @@ def run_dist(args, lg, rank, world, local_rank, dev, barrier):
     d = FusedDistributedFFT(n)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = torch.view_as_complex(torch.empty((n // world, 2), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g))
+    if d.input is not None:          # pull layouts: the input lives in the plan's peer-visible array (no local copy)
+        d.input.copy_(x)
+        x = d.input
     for _ in range(max(3, min(args.warmup, 10))):
         d.forward(x)
     barrier()

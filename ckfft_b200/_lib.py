@@ -34,7 +34,7 @@ class Plan(C.Structure):
 class DistLayout(C.Structure):
     """CkFftB200DistLayout"""
     _fields_ = [("log2n", C.c_int), ("world", C.c_int), ("log2n1", C.c_int), ("log2n2", C.c_int), ("la", C.c_int),
-                ("lb", C.c_int), ("lc", C.c_int), ("ld", C.c_int), ("passes", C.c_int)]
+                ("lb", C.c_int), ("lc", C.c_int), ("ld", C.c_int), ("passes", C.c_int), ("pull", C.c_int)]
 
 
 class DistPass(C.Structure):
@@ -42,7 +42,9 @@ class DistPass(C.Structure):
     _fields_ = [("kind", C.c_int), ("routed", C.c_int), ("L", C.c_int), ("nproblems", C.c_longlong), ("ncols", C.c_int),
                 ("twLog2", C.c_int), ("twColBase", C.c_int), ("twColShift", C.c_int), ("kProbMul", C.c_int),
                 ("kMul", C.c_int), ("rankShift", C.c_int), ("outRowStride", C.c_longlong), ("outColBase", C.c_longlong),
-                ("inColStride", C.c_longlong), ("inProbStride", C.c_longlong), ("src", C.c_int), ("dst", C.c_int)]
+                ("inColStride", C.c_longlong), ("inProbStride", C.c_longlong), ("src", C.c_int), ("dst", C.c_int),
+                ("pull", C.c_int), ("pullRows", C.c_int), ("pullRowLen", C.c_longlong), ("pullN2", C.c_longlong),
+                ("pullCol0", C.c_longlong), ("pullW", C.c_int)]
 
 
 _lib = None
@@ -95,7 +97,8 @@ def load() -> C.CDLL:
     lib.CkFftB200PeerClose.restype = None
     lib.CkFftB200PeerClose.argtypes = [vp]
     lib.CkFftB200DistPlanCreate.restype = vp
-    lib.CkFftB200DistPlanCreate.argtypes = [vp, C.c_longlong, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.CkFftB200DistPlanCreate.argtypes = [vp, C.c_longlong, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                            C.POINTER(vp)]
     lib.CkFftB200DistExecAsync.argtypes = [vp, vp, i, vp]
     lib.CkFftB200DistPlanStatus.argtypes = [vp]
     lib.CkFftB200DistPlanSetProfiling.argtypes = [vp, i]

@@ -856,7 +856,8 @@ struct CkFftB200DistPlan
 };
 
 CkFftB200DistPlan* CkFftB200DistPlanCreate(CkFftContext* c, long long n, int rank, int world, int preferPasses,
-                                           void* const* work, void* const* mid, void* const* out, void* const* flags)
+                                           void* const* work, void* const* mid, void* const* out, void* const* flags,
+                                           void* const* in)
 {
     if (!c || c->magic != kMagic) { set_error("invalid context"); return NULL; }
     if (!c->fwdExpTable && !c->invExpTable) { set_error("invalid context"); return NULL; }
@@ -882,6 +883,20 @@ CkFftB200DistPlan* CkFftB200DistPlanCreate(CkFftContext* c, long long n, int ran
     p->layout = lay;
     p->rank = rank;
     p->epoch = 0;
+    if (in) {
+        // pull mode: tensor maps over every rank's input array, built once
+        DeviceGuard guard(c->device);
+        for (int q = 0; q < world; ++q) {
+            if (!in[q] || ((uintptr_t) in[q] & 127)) { set_error("distributed plan: input arrays must be non-NULL and 128-byte aligned"); free(p); return NULL; }
+            p->bufs.in[q] = (ckb::cf*) in[q];
+        }
+        p->layout.pull = 1;
+        void* dmaps = NULL;
+        cudaError_t e = cudaMalloc(&dmaps, 128 * CKB_MAX_PEERS);
+        if (e == cudaSuccess) e = ckb::dist_make_pull_maps(p->layout, rank, p->bufs.in, (::CUtensorMap_st*) dmaps, &p->bufs.pull_box_rows);
+        if (e != cudaSuccess) { set_error("distributed plan: tensor maps of the input arrays", e); if (dmaps) cudaFree(dmaps); free(p); return NULL; }
+        p->bufs.pull_maps = (const ::CUtensorMap_st*) dmaps;
+    }
     return p;
 }
 
@@ -950,6 +965,7 @@ void CkFftB200DistPlanDestroy(CkFftB200DistPlan* p)
 {
     if (!p || p->magic != kMagic) return;
     CkFftB200DistPlanSetProfiling(p, 0);
+    if (p->bufs.pull_maps) { DeviceGuard guard(p->ctx->device); cudaFree((void*) p->bufs.pull_maps); }
     p->magic = 0;
     free(p);
 }

@@ -71,11 +71,20 @@ int dist_describe(const CkFftB200DistLayout& l, int rank, CkFftB200DistPass pass
     const long long n1 = 1LL << l.log2n1, n2 = 1LL << l.log2n2;
     const long long h = n1 / l.world, w = n2 / l.world;
     int np = 0;
+    auto set_pull = [&](CkFftB200DistPass& f) {            // the first pass reads the ranks' input arrays directly
+        if (!l.pull) return;
+        f.pull = 1;
+        f.pullRows = f.L / l.world;
+        f.pullRowLen = (long long) (f.ncols / w) * n2;
+        f.pullN2 = n2; f.pullCol0 = rank * w; f.pullW = (int) w;
+        f.src = 3;
+    };
     if (l.la > 1) {
         CkFftB200DistPass a{};
         a.kind = KIND_COLUMN; a.routed = 0; a.L = l.la; a.nproblems = 1; a.ncols = (int) (l.lb * w);
         a.twLog2 = l.log2n1; a.twColBase = 0; a.twColShift = host_ilog2(w);
         a.src = 0; a.dst = 2;
+        set_pull(a);
         passes[np++] = a;
     }
     {
@@ -85,6 +94,7 @@ int dist_describe(const CkFftB200DistLayout& l, int rank, CkFftB200DistPass pass
         b.kProbMul = l.la > 1 ? 1 : 0; b.kMul = l.la; b.rankShift = host_ilog2(h);
         b.outRowStride = n2; b.outColBase = rank * w;
         b.src = l.la > 1 ? 2 : 0; b.dst = 1;
+        if (l.la == 1) set_pull(b);
         passes[np++] = b;
     }
     if (l.lc > 1) {
@@ -173,6 +183,35 @@ static cudaError_t launch_routed_pass(bool inverse, int kind, int L, const TileP
     return inverse ? launch_tile<true, KIND_LAST, true>(L, p, s) : launch_tile<false, KIND_LAST, true>(L, p, s);
 }
 
+// C columns / TMA box rows of the tile plan for length L (tile_launch.h)
+static bool tile_plan_of(int L, int* C, int* box_rows)
+{
+#define X(L_, E_, R0_, R1_, C_, MINB_) \
+    if (L == L_) { *C = C_; *box_rows = TileCfg<L_, E_, R0_, R1_, C_, false, KIND_COLUMN, MINB_, true, true>::BOX_ROWS; return true; }
+    CKB_TILE_PLANS(X)
+#undef X
+    return false;
+}
+
+// Pull mode: one tensor map per rank over its input array as the first pass sees it, [L/P][rowLen], boxes of
+// [min(L/P, box rows)][C]; uploaded once to `dmaps` (device memory, world entries).
+cudaError_t dist_make_pull_maps(const CkFftB200DistLayout& l, int rank, cf* const* in, CUtensorMap* dmaps, int* box_rows_out)
+{
+    CkFftB200DistPass passes[4];
+    dist_describe(l, rank, passes);
+    const CkFftB200DistPass& f = passes[0];
+    if (!f.pull) return cudaErrorInvalidValue;
+    int C = 0, box = 0;
+    if (!tile_plan_of(f.L, &C, &box)) return cudaErrorInvalidValue;
+    if (box > f.pullRows) box = f.pullRows;
+    CUtensorMap host[CKB_MAX_PEERS];
+    memset(host, 0, sizeof(host));
+    for (int q = 0; q < l.world; ++q)
+        if (f.pullRowLen >= (1LL << 31) || !make_tile_map(&host[q], in[q], f.pullRows, (int) f.pullRowLen, box, C)) return cudaErrorInvalidValue;
+    *box_rows_out = box;
+    return cudaMemcpy(dmaps, host, sizeof(CUtensorMap) * l.world, cudaMemcpyHostToDevice);
+}
+
 cudaError_t dist_exec(const CkFftB200DistLayout& l, int rank, const DistBuffers& b, unsigned* epoch, const cf* in_local,
                       bool inverse, const cf* table, int log2_nt, const BigTwiddles& tw, cudaStream_t s, DistMarks* marks)
 {
@@ -186,7 +225,13 @@ cudaError_t dist_exec(const CkFftB200DistLayout& l, int rank, const DistBuffers&
         marks->name[marks->count++] = name;
     };
     mark("start");
-    {
+    if (l.pull) {
+        // no exchange kernel: the input only has to sit in the peer-visible array before the barrier
+        if (in_local != b.in[rank]) {
+            if ((e = cudaMemcpyAsync(b.in[rank], in_local, (size_t) (h * n2) * sizeof(cf), cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
+            mark("copy-in");
+        }
+    } else {
         PeerPtrs work{};
         for (int q = 0; q < l.world; ++q) work.p[q] = b.buf[0][q];
         const long long units = h * n2 / 2;
@@ -197,8 +242,8 @@ cudaError_t dist_exec(const CkFftB200DistLayout& l, int rank, const DistBuffers&
                                                           host_ilog2(w / 2), (long long) rank * h);
         count_launch();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        mark("exchange");
     }
-    mark("exchange");
     if ((e = launch_barrier(b, rank, l.world, ++*epoch, s)) != cudaSuccess) return e;
     mark("barrier");
 
@@ -207,7 +252,7 @@ cudaError_t dist_exec(const CkFftB200DistLayout& l, int rank, const DistBuffers&
     for (int i = 0; i < np; ++i) {
         const CkFftB200DistPass& d = passes[i];
         TileParams p{};
-        p.in = b.buf[d.src][rank];
+        p.in = d.src == 3 ? b.in[rank] : b.buf[d.src][rank];
         p.out = b.buf[d.dst][rank];
         p.table = table; p.log2_nt = log2_nt;
         p.tw_lo = tw.lo; p.tw_hi = tw.hi; p.tw_h = tw.h;
@@ -215,18 +260,32 @@ cudaError_t dist_exec(const CkFftB200DistLayout& l, int rank, const DistBuffers&
         p.nproblems = d.nproblems; p.ncols = d.ncols; p.P = 1; p.Q = 1;
         p.stream_in = 1; p.stream_out = d.routed ? 1 : 0;
         p.tw_col_shift = d.twColShift; p.tw_col_base = d.twColBase;
-        if (d.routed) {
-            for (int q = 0; q < l.world; ++q) p.peer[q] = b.buf[d.dst][q];
-            p.k_prob_mul = d.kProbMul; p.k_mul = d.kMul; p.rank_shift = d.rankShift;
-            p.out_row_stride = d.outRowStride; p.out_col_base = d.outColBase;
-            p.in_col_stride = d.inColStride; p.in_prob_stride = d.inProbStride;
+        const char* name = d.routed ? (d.kind == KIND_COLUMN ? "passB(push)" : "passD(push)") : (d.dst == 2 ? "passA" : "passC");
+        if (d.pull) {
+            p.pull_maps = b.pull_maps; p.pull_rows = d.pullRows; p.pull_box_rows = b.pull_box_rows;
+            p.pull_w_shift = host_ilog2(d.pullW); p.pull_n2 = d.pullN2; p.pull_col0 = d.pullCol0;
+            name = d.routed ? "passB(pull+push)" : "passA(pull)";
+        }
+        if (d.routed || d.pull) {
+            if (d.routed) {
+                for (int q = 0; q < l.world; ++q) p.peer[q] = b.buf[d.dst][q];
+                p.k_prob_mul = d.kProbMul; p.k_mul = d.kMul; p.rank_shift = d.rankShift;
+                p.out_row_stride = d.outRowStride; p.out_col_base = d.outColBase;
+                p.in_col_stride = d.inColStride; p.in_prob_stride = d.inProbStride;
+            } else {
+                // a local pass run by the routed kernel (it is the one that can pull): every row stays here
+                p.peer[0] = p.out; p.k_prob_mul = 0; p.k_mul = 1; p.rank_shift = 30;
+                p.out_row_stride = d.ncols; p.out_col_base = 0;
+            }
             e = launch_routed_pass(inverse, d.kind, d.L, p, s);
-            mark(d.kind == KIND_COLUMN ? "passB(push)" : "passD(push)");
-            if (e == cudaSuccess) e = launch_barrier(b, rank, l.world, ++*epoch, s);
-            mark("barrier");
+            mark(name);
+            if (e == cudaSuccess && d.routed) {
+                e = launch_barrier(b, rank, l.world, ++*epoch, s);
+                mark("barrier");
+            }
         } else {
             e = launch_local_pass(inverse, d.kind, d.L, p, s);
-            mark(d.src == 0 ? "passA" : "passC");
+            mark(name);
         }
         if (e != cudaSuccess) return e;
     }

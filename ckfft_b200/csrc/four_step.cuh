@@ -58,6 +58,12 @@ struct TileParams {
     long long out_row_stride;
     long long out_col_base;
     long long in_col_stride, in_prob_stride;
+    // pull (first pass of the fused distributed transform): the [L][ncols] problem is spread over the ranks' input
+    // arrays, rank s holding rows [s*pull_rows, (s+1)*pull_rows) as a 2-D tensor described by pull_maps[s] (device
+    // memory); tile column c0 is that tensor's column (c0 >> pull_w_shift) * pull_n2 + pull_col0 + (c0 & (w - 1)).
+    const CUtensorMap* pull_maps;
+    int pull_rows, pull_box_rows, pull_w_shift;
+    long long pull_n2, pull_col0;
 };
 
 __device__ __forceinline__ cf ld_sel(const cf* p, int stream) { return stream ? __ldcs(p) : __ldg(p); }
@@ -169,9 +175,15 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(mbar, L * C * 8);
         if constexpr (TC::KIND == KIND_COLUMN) {
+            if (TC::RT && p.pull_maps) {                       // rows come from the peers' input arrays, over NVLink
+                const int x0 = (int) ((c0 >> p.pull_w_shift) * p.pull_n2 + p.pull_col0) + (c0 & ((1 << p.pull_w_shift) - 1));
+                for (int r0 = 0; r0 < L; r0 += p.pull_box_rows)
+                    tensor_load_2d(xall + r0 * C, p.pull_maps + r0 / p.pull_rows, x0, r0 % p.pull_rows, mbar);
+            } else {
 #pragma unroll
-            for (int r0 = 0; r0 < L; r0 += TC::BOX_ROWS)
-                tensor_load_2d(xall + r0 * C, &tmap_in, c0, (int) (prob * L + r0), mbar);
+                for (int r0 = 0; r0 < L; r0 += TC::BOX_ROWS)
+                    tensor_load_2d(xall + r0 * C, &tmap_in, c0, (int) (prob * L + r0), mbar);
+            }
         } else {
 #pragma unroll
             for (int g = 0; g < C; ++g) bulk_load(xall + g * L, last_src(prob, c0 + g), L * 8, mbar, l2pol);

@@ -4,6 +4,8 @@
 #include "fft_kernel.cuh"
 #include "ckfft/ckfft_b200.h"
 
+struct CUtensorMap_st;                 // <cuda.h>; only pointers to it cross this interface
+
 namespace ckb {
 
 // one variant per translation unit (fft_variants.cu is compiled four times)
@@ -49,7 +51,11 @@ cudaError_t launch_twiddle_rows(cf* data, long long rows, long long cols, long l
 struct DistBuffers {
     cf* buf[3][CKB_MAX_PEERS];          // [work, mid, out][rank]
     unsigned* flags[CKB_MAX_PEERS];     // per rank: arrive[CKB_MAX_PEERS] + error word
+    cf* in[CKB_MAX_PEERS];              // pull mode: every rank's peer-visible input array
+    const ::CUtensorMap_st* pull_maps;   // pull mode: device array of `world` tensor maps over those arrays
+    int pull_box_rows;
 };
+cudaError_t dist_make_pull_maps(const CkFftB200DistLayout& l, int rank, cf* const* in, ::CUtensorMap_st* dmaps, int* box_rows_out);
 bool dist_layout(long long n, int world, int prefer, CkFftB200DistLayout* out);
 int dist_describe(const CkFftB200DistLayout& l, int rank, CkFftB200DistPass passes[4]);
 struct DistMarks {                      // optional per-phase events of one execution (profiling)

@@ -132,6 +132,7 @@ typedef struct
     int la, lb;               /* n1 = la * lb (la = 1: n1 is one pass) */
     int lc, ld;               /* n2 = lc * ld (lc = 1: n2 is one pass) */
     int passes;               /* FFT passes over the data (2 .. 4), not counting the exchange */
+    int pull;                 /* 1: no exchange kernel -- the first pass fetches its tiles from the peers' input arrays (TMA) */
 } CkFftB200DistLayout;
 
 /* One FFT pass as the tile kernel sees it (the CPU tests replay these descriptors in numpy). */
@@ -151,6 +152,11 @@ typedef struct
     long long inColStride;    /* routed kind 1: column c of problem q starts at c*inColStride + q*inProbStride */
     long long inProbStride;
     int src, dst;             /* 0 work, 1 mid, 2 out */
+    int pull;                 /* 1 (first pass of a pull layout): row a of the [L][ncols] problem is row a % pullRows of   */
+    int pullRows;             /*   rank a / pullRows's INPUT array viewed as [pullRows][pullRowLen], and column c is its    */
+    long long pullRowLen;     /*   element (c / pullW) * pullN2 + pullCol0 + c % pullW                                       */
+    long long pullN2, pullCol0;
+    int pullW;
 } CkFftB200DistPass;
 
 /* Pure host arithmetic (no GPU needed).  preferPasses: 0 = default, 3 or 4 forces that pass count where possible.
@@ -168,9 +174,13 @@ void CkFftB200PeerClose(void* p);
 
 typedef struct CkFftB200DistPlan CkFftB200DistPlan;
 /* work/mid/out/flags: arrays of `world` device pointers, entry q = rank q's buffer (own allocation at q == rank).
+ * `in` (may be NULL): a fourth array of n/world complex per rank.  When given, the plan runs in PULL mode: there is no
+ * exchange kernel, the first FFT pass fetches its tiles straight from the peers' `in` arrays with TMA; an execution
+ * whose input is not the rank's own `in` array copies it there first.
  * The context must have been created with nMax >= n (it carries the twiddles of W_n). */
 CkFftB200DistPlan* CkFftB200DistPlanCreate(CkFftContext* context, long long n, int rank, int world, int preferPasses,
-                                           void* const* work, void* const* mid, void* const* out, void* const* flags);
+                                           void* const* work, void* const* mid, void* const* out, void* const* flags,
+                                           void* const* in);
 /* Enqueue one transform of this rank's slice `input` (n/world complex, device memory, not one of the plan's
  * buffers) on `stream`.  inverse != 0: un-normalised inverse.  Returns 1 if everything was enqueued. */
 int CkFftB200DistExecAsync(CkFftB200DistPlan* plan, const CkFftComplex* input, int inverse, void* stream);

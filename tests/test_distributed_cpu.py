@@ -110,13 +110,16 @@ def test_fused_layout_rules():
 @pytest.mark.parametrize("shape", [(1, 128, 1, 128, 1), (1, 128, 1, 128, 8), (1, 128, 128, 128, 2), (16, 16, 16, 16, 2),
                                    (8, 32, 16, 8, 4), (1, 64, 8, 16, 2), (16, 8, 1, 128, 8)])
 @pytest.mark.parametrize("inverse", [False, True])
-def test_fused_replay_matches_fft(shape, inverse):
-    """All ranks simulated in one process: exchange + pass descriptors reproduce the N-point transform."""
+@pytest.mark.parametrize("pull", [False, True])
+def test_fused_replay_matches_fft(shape, inverse, pull):
+    """All ranks simulated in one process: exchange (push layouts) or peer reads of the first pass (pull layouts) +
+    the pass descriptors reproduce the N-point transform."""
     from ckfft_b200.distributed import fused_layout, replay_fused
 
     la, lb, lc, ld, world = shape
     lay = fused_layout(la * lb * lc * ld, world) if min(lb, ld) >= 128 and la in (1,) and lc in (1, 128) else \
         _synthetic_layout(la, lb, lc, ld, world)
+    lay.pull = int(pull)
     assert (lay.la, lay.lb, lay.lc, lay.ld) == (la, lb, lc, ld)
     n = 1 << lay.log2n
     rng = np.random.default_rng(3)
@@ -148,12 +151,13 @@ def _fused_worker(rank, world, port, tmpdir):
         my_bufs[buf_id][ridx.numpy()] = rval.numpy().view(np.complex64)
 
     ok = True
-    for n in (1 << 14, 1 << 21):
-        lay = fused_layout(n, world)
+    for n, pull in ((1 << 14, False), (1 << 21, False), (1 << 21, True)):
+        lay = fused_layout(n, world, pull=pull)
         rng = np.random.default_rng(11)
         x = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)      # same on every rank
         per = n // world
-        slices = {rank: x[rank * per:(rank + 1) * per]}
+        # push layouts touch only this rank's slice; a pull layout reads the peers' input arrays (here: their copies)
+        slices = {q: x[q * per:(q + 1) * per] for q in (range(world) if pull else [rank])}
         mine = replay_fused(slices, lay, False, deliver=deliver, ranks=[rank])[0]
         parts = [None] * world
         dist.all_gather_object(parts, mine)

@@ -443,15 +443,19 @@ def test_six_step_glue_kernels():
 # exchange kernel, the flag barrier and every routed tile kernel run exactly as they do across NVLink)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("log2n", [14, 15, 17, 20, 21, 23, 24])
-def test_fused_distributed_single_rank(log2n):
+@pytest.mark.parametrize("pull", [False, True])
+def test_fused_distributed_single_rank(log2n, pull):
     from ckfft_b200.distributed import FusedDistributedFFT
 
     n = 1 << log2n
     rng = np.random.default_rng(log2n)
     x = uniform_complex(rng, (n,))
     want = oracle.fp64_c2c(x)
-    d = FusedDistributedFFT(n)
+    d = FusedDistributedFFT(n, pull=pull)
     xd = torch.from_numpy(x).cuda()
+    if pull and log2n % 2:
+        d.input.copy_(xd)            # the zero-copy way: the caller fills the plan's own input array
+        xd = d.input
     y = d.forward(xd).clone()
     assert rel_rms(y.cpu().numpy(), want) <= tolerance(n)
     z = d.inverse(y)
@@ -460,13 +464,13 @@ def test_fused_distributed_single_rank(log2n):
     d.close()
 
 
-@pytest.mark.parametrize("prefer", [3, 4])
-def test_fused_distributed_2_28_analytic(prefer):
+@pytest.mark.parametrize("prefer,pull", [(3, False), (4, False), (4, True)])
+def test_fused_distributed_2_28_analytic(prefer, pull):
     """Four-pass and three-pass layouts at 2^28 points: closed-form spectrum of exponentials + an impulse."""
     from ckfft_b200.distributed import FusedDistributedFFT
 
     n = 1 << 28
-    d = FusedDistributedFFT(n, prefer_passes=prefer)
+    d = FusedDistributedFFT(n, prefer_passes=prefer, pull=pull)
     assert d.layout.passes == prefer
     idx = torch.arange(n, device="cuda", dtype=torch.float64)
     freqs, amps, n0 = [3, n // 3 + 1, n - 7], [1.0, 0.5, 0.25], 5
@@ -502,7 +506,7 @@ def test_fused_distributed_rejects_bad_arguments():
     assert lib.CkFftB200DistExecAsync(None, x.data_ptr(), 0, None) == 0
     with ck.Context(1 << 12, ck.BOTH) as small:                                      # context too small for n
         arr = (C.c_void_p * 1)(d._own[0])
-        assert not lib.CkFftB200DistPlanCreate(small.handle, 1 << 14, 0, 1, 0, arr, arr, arr, arr)
+        assert not lib.CkFftB200DistPlanCreate(small.handle, 1 << 14, 0, 1, 0, arr, arr, arr, arr, None)
     d.close()
 
 
@@ -547,12 +551,12 @@ def _fused_two_rank_worker(rank, world, port, tmpdir, ndev):
     torch.cuda.set_device(rank % ndev)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     ok = True
-    for log2n in (14, 21):
+    for log2n, pull in ((14, False), (21, False), (14, True), (21, True)):
         n = 1 << log2n
         rng = np.random.default_rng(100 + log2n)
         x = uniform_complex(rng, (n,))                                   # same on every rank
         per = n // world
-        d = FusedDistributedFFT(n)
+        d = FusedDistributedFFT(n, pull=pull)
         xd = torch.from_numpy(x[rank * per:(rank + 1) * per]).cuda()
         y = d.forward(xd).clone()
         z = d.inverse(y).clone()

@@ -2,7 +2,8 @@
 """Check + timing of the FUSED distributed transform (peer stores over NVLink, no collective on the data path).
     python tools/fused_check.py [log2n ...]                                   one GPU (world 1: every "peer" is the GPU itself)
     python -m torch.distributed.run --nproc-per-node P --master-addr 127.0.0.1 tools/fused_check.py [log2n ...]
-Options: --passes 3|4 (force a pass count), --no-nccl (skip the comparison with the NCCL six-step), --phases.
+Options: --passes 3|4 (force a pass count), --no-nccl (skip the comparison with the NCCL six-step), --push / --pull (exchange kernel first,
+or a first pass that pulls its tiles from the peers; default: pull for four-pass layouts).
 Parity: analytic input (complex exponentials + an impulse, closed-form spectrum), round trip, Parseval, the full fp64
 spectrum for N <= 2^24, and element-wise agreement with the NCCL six-step of ckfft_b200.distributed on the same input."""
 import os
@@ -23,6 +24,7 @@ def main():
     if "--passes" in args:
         i = args.index("--passes"); prefer = int(args[i + 1]); del args[i:i + 2]
     with_nccl = "--no-nccl" not in args
+    pull = False if "--push" in args else (True if "--pull" in args else None)
     args = [a for a in args if not a.startswith("--")]
     multi = "RANK" in os.environ
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
@@ -46,8 +48,9 @@ def main():
     for lg in sizes:
         n = 1 << lg
         per = n // world
-        d = FusedDistributedFFT(n, prefer_passes=prefer)
+        d = FusedDistributedFFT(n, prefer_passes=prefer, pull=pull)
         lay = d.layout
+        pull_now = bool(lay.pull)
         idx = torch.arange(rank * per, (rank + 1) * per, device=dev, dtype=torch.float64)
         freqs, amps, n0 = [3, n // 3 + 1, n - 7], [1.0, 0.5, 0.25], 5
         x = torch.zeros(per, dtype=torch.complex128, device=dev)
@@ -115,6 +118,9 @@ def main():
                     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
                 ms_nccl = float(ms.item())
                 dn.close()
+        if pull_now:
+            d.input.copy_(noise)                 # timed the zero-copy way: the input lives in the plan's peer-visible array
+            noise = d.input
         for _ in range(3):
             d.forward(noise)
         sync()
@@ -137,7 +143,7 @@ def main():
             tol = 1e-6 * lg
             ms = float(ms.item())
             fmt = lambda v: "None" if v is None else format(v, ".2e")
-            print(f"FUSED N=2^{lg} P={world} passes={lay.passes} ({lay.la}x{lay.lb} . {lay.lc}x{lay.ld}): analytic {err_analytic:.2e} "
+            print(f"FUSED{'(pull)' if pull_now else '(push)'} N=2^{lg} P={world} passes={lay.passes} ({lay.la}x{lay.lb} . {lay.lc}x{lay.ld}): analytic {err_analytic:.2e} "
                   f"roundtrip {err_rt:.2e} parseval {pars:.1e} full-fp64 {fmt(err_full)} vs-nccl-six-step {fmt(err_nccl)} (tol {tol:.1e}) | "
                   f"{ms:.3f} ms = {16.0 * n / world / ms / 1e6:.1f} GB/s per GPU algorithmic, {5.0 * n * lg / ms / 1e6:.0f} GFLOP/s, "
                   f"exchange {d.bytes_per_exchange() / 1e6:.1f} MB/GPU x3"
