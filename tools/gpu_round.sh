@@ -2,7 +2,7 @@
 # One GPU-box visit: smoke, bench (both arms), ncu launch list of the bench command, ncu --set full of the top kernel.
 set -x
 mkdir -p gpurun_out
-TAG=${1:-r1}
+TAG=${1:-r1d}
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; tail -c 3000 gpurun_out/bench_${TAG}.json; tail -5 gpurun_out/bench_${TAG}.err
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref_${TAG}.json 2>&1; tail -c 1500 gpurun_out/bench_ref_${TAG}.json
