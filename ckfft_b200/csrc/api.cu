@@ -115,6 +115,12 @@ size_t l2_group_bytes()
     return bytes;
 }
 
+bool getenv_flag(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return (e && *e ? atoi(e) : dflt) != 0;
+}
+
 ckb::BigTwiddles big_tw(const _CkFftContext* c) { return ckb::BigTwiddles{ c->dTwLo, c->dTwHi, c->twH, c->log2Tmax }; }
 
 cudaError_t enqueue_large_c2c(const _CkFftContext* c, bool inv, int n, const ckb::cf* in, ckb::cf* out, long long batch,
@@ -157,6 +163,17 @@ cudaError_t enqueue_large_real(const _CkFftContext* c, bool inverse, int n, cons
     const int M = n / 2;
     if ((!inverse && (in_stride != n || out_stride != M + 1)) || (inverse && (in_stride != M + 1 || out_stride != n)))
         return cudaErrorNotSupported;
+    if (!inverse && M <= (1 << 20) && ckb::pipe_enabled() && getenv_flag("CKFFT_B200_PIPE_REAL", 1) && (((uintptr_t) in) & 15) == 0) {
+        // real forward: half-length complex transform + split in ONE dataflow kernel (pipe_kernel.cuh, PipeCfg::REAL)
+        const long long chunk = 1LL << 20;
+        cudaError_t e = cudaSuccess;
+        for (long long done = 0; done < batch && e == cudaSuccess; done += chunk) {
+            const long long cnt = batch - done < chunk ? batch - done : chunk;
+            e = ckb::launch_pipe_r2c(ilog2i(M), (const cf*) ((const float*) in + done * n), (cf*) out + done * (M + 1), cnt, M + 1,
+                                     c->dTable, c->log2Table, big_tw(c), s);
+        }
+        return e;
+    }
     const size_t per = (size_t) M * sizeof(cf);
     long long sub = (long long) (kScratchCapBytes / per);
     if (sub < 1) sub = 1;

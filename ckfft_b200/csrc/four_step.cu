@@ -89,13 +89,13 @@ bool pipe_enabled()
     return env_ll("CKFFT_B200_PIPE", 1) != 0 && tensor_map_encoder() != nullptr;   // read per call: tests flip it
 }
 
-template <int L0, int L1, int MINB, bool INV, int NBUF>
+template <int L0, int L1, int MINB, bool INV, int NBUF, bool REAL = false>
 static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const cf* table, int log2_nt, const BigTwiddles& tw,
-                                   cudaStream_t s)
+                                   cudaStream_t s, long long out_stride = 0)
 {
     using A = typename PipeTile<L0, INV, KIND_COLUMN>::type;
     using B = typename PipeTile<L1, INV, KIND_LAST>::type;
-    using PC = PipeCfg<A, B, MINB, NBUF>;
+    using PC = PipeCfg<A, B, MINB, NBUF, REAL>;
     auto kern = pipe_kernel<PC, A, B>;
     constexpr int CTA = PC::THREADS + 64;                    // consumers + loader warp + signaller warp
     static int grid_cap[64] = {0};
@@ -147,6 +147,9 @@ static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const
     p.tw_lo = tw.lo; p.tw_hi = tw.hi; p.tw_h = tw.h; p.tw_shift = tw.log2_tmax - ilog2(L0) - ilog2(L1);
     p.batch = batch; p.ring_slots = (int) slots; p.lag = (int) lag;
     p.ticket = ctr; p.done1 = ctr + 4; p.done2 = ctr + 4 + batch;
+    p.out_stride = out_stride ? out_stride : N + 1;
+    p.tw_shift_real = tw.log2_tmax - ilog2(L0) - ilog2(L1) - 1;
+    if (REAL && p.tw_shift_real < 0) { cudaFreeAsync(ws, s); return cudaErrorInvalidValue; }
     kern<<<grid, CTA, PC::SMEM_BYTES, s>>>(p, tmap);
     count_launch();
     e = cudaGetLastError();
@@ -170,6 +173,21 @@ cudaError_t launch_pipe(bool inverse, int log2n, const cf* in, cf* out, long lon
         return inverse ? launch_pipe_cfg<L0_, L1_, MINB_, true, 1>(in, out, batch, table, log2_nt, tw, s) \
                        : launch_pipe_cfg<L0_, L1_, MINB_, false, 1>(in, out, batch, table, log2_nt, tw, s); \
     }
+    CKB_PIPE_PLANS(X)
+#undef X
+    return cudaErrorNotSupported;
+}
+
+// `batch` real forward transforms of n = 2 * 2^log2m points: in = the real input viewed as 2^log2m complex values per
+// frame (dense), out = half spectra of out_stride complex each.  The split is fused into pass 2 of the dataflow kernel.
+cudaError_t launch_pipe_r2c(int log2m, const cf* in, cf* out, long long batch, long long out_stride, const cf* table, int log2_nt,
+                            const BigTwiddles& tw, cudaStream_t s)
+{
+    int npass, L[3];
+    four_step_plan(log2m, &npass, L);
+    if (npass != 2 || ((uintptr_t) in & 15)) return cudaErrorNotSupported;
+#define X(L0_, L1_, MINB_) \
+    if (L[0] == L0_ && L[1] == L1_) return launch_pipe_cfg<L0_, L1_, MINB_, false, 1, true>(in, out, batch, table, log2_nt, tw, s, out_stride);
     CKB_PIPE_PLANS(X)
 #undef X
     return cudaErrorNotSupported;

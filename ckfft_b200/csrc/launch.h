@@ -33,6 +33,8 @@ cudaError_t launch_four_step(bool inverse, int log2n, const cf* in, cf* out, cf*
 bool pipe_enabled();                  // two-pass lengths as one L2-resident dataflow kernel (pipe_kernel.cuh)
 cudaError_t launch_pipe(bool inverse, int log2n, const cf* in, cf* out, long long batch, const cf* table, int log2_nt,
                         const BigTwiddles& tw, cudaStream_t s);
+cudaError_t launch_pipe_r2c(int log2m, const cf* in, cf* out, long long batch, long long out_stride, const cf* table, int log2_nt,
+                            const BigTwiddles& tw, cudaStream_t s);
 cudaError_t launch_real_split(const cf* z, cf* y, int n, long long batch, long long z_stride, long long y_stride,
                               const BigTwiddles& tw, cudaStream_t s);
 cudaError_t launch_real_twist(const cf* y, cf* t, int n, long long batch, long long y_stride, long long t_stride,

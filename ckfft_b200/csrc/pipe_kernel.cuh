@@ -42,6 +42,9 @@ struct PipeParams {
     unsigned* ticket;
     unsigned* done1;        // [batch]
     unsigned* done2;        // [batch]
+    // real-forward kernels (PipeCfg::REAL): `in` is the real input viewed as M complex, `out` the half spectrum
+    long long out_stride;   // complex elements per output row (M + 1 by default)
+    int tw_shift_real;      // scales an exponent of W_(2M) to one of W_Tmax
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p)
@@ -74,8 +77,13 @@ __device__ __forceinline__ cf pipe_twiddle(const PipeParams& p, unsigned c, unsi
 }
 
 // A: column-pass plan (L0, C0 columns of the [L0][L1] problem per tile), B: last-pass plan (L1, C1 contiguous columns)
-template <class A, class B, int MINB_, int NBUF_ = 1>
+template <class A, class B, int MINB_, int NBUF_ = 1, bool REAL_ = false>
 struct PipeCfg {
+    // REAL: real forward transform of 2M points = this M-point complex transform + the split
+    //   Y[k] = (Z[k] + conj Z[M-k]) - i W_2M^k (Z[k] - conj Z[M-k])        (src/ckfft/fft_real_default.cpp:13-63)
+    // fused into pass 2: a tile holds C/2 columns c and their mirrors L0 - c (columns 0 and L0/2 mirror themselves),
+    // so Z[k] and Z[M-k] meet in the tile and the half spectrum is the only thing written to HBM.
+    static constexpr bool REAL = REAL_;
     static constexpr int NBUF = NBUF_;            // tile buffers (each is staging area, then exchange buffer, of one item)
     static_assert(NBUF_ == 1 || NBUF_ == 2, "one buffer, or two in ping-pong");
     static_assert(A::THREADS == B::THREADS, "both passes run in the same CTA");
@@ -150,6 +158,17 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
         pass = 2; prob = (p.batch - lag) + (long long) (t / T2); c0 = (int) (t % T2) * B::C;
     };
 
+    // pass-2 column held by slot g of the tile that starts at c0.  Complex kernels: c0 + g.  Real kernels: slots
+    // [0, C/2) hold columns c0/2 + g, slots [C/2, C) their mirrors L0 - (c0/2 + g); the first tile pairs the two
+    // self-mirrored columns, 0 and L0/2.
+    auto pass2_column = [&](int c0, int g) -> int {
+        if constexpr (!PC::REAL) return c0 + g;
+        constexpr int H = B::C / 2;
+        const int c = c0 / 2 + (g & (H - 1));
+        if (g < H) return c;
+        return c == 0 ? L0 / 2 : L0 - c;
+    };
+
     if (tid >= THREADS) {
         // ---------------- two service warps (one lane each): loader and signaller ----------------
         // No global round trip (ticket atomic, dependency poll, the fence before a completion counter) sits on the
@@ -212,7 +231,7 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
                 mbar_expect_tx(full, L1 * B::C * 8);
                 const cf* slot = p.ring + (prob % p.ring_slots) * N;
 #pragma unroll
-                for (int g = 0; g < B::C; ++g) bulk_load(stage + g * L1, slot + (long long) (c0 + g) * L1, L1 * 8, full, pol_keep);
+                for (int g = 0; g < B::C; ++g) bulk_load(stage + g * L1, slot + (long long) pass2_column(c0, g) * L1, L1 * 8, full, pol_keep);
             }
         };
         // item j goes into buffer j % NBUF, which item j - NBUF must have drained; the signaller is kept within one item
@@ -299,18 +318,67 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
             stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xb + g0 * XBUF, j0, true);
             consumer_sync();
             stage_gather<L, T, E, R1, LOGPAD, SRC_XBUF>(v, nullptr, xb + g1 * XBUF, j1, true);
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bfree)) : "memory");
-            stage_math<T, E, R1, R0, INV, TW_LUT>(v, lutB, p.table, 0, j1);
             constexpr int B1 = E / R1, STR1 = L / R1;
-            cf* ocol = p.out + prob * N + c0 + g1;
-            static_for<0, B1>([&](auto q_) {
-                constexpr int q = decltype(q_)::value;
-                const int jq = j1 + q * T;
-                static_for<0, R1>([&](auto u_) {
-                    constexpr int u = decltype(u_)::value;
-                    __stcs(ocol + (long long) (jq + u * STR1) * L0, v[q * R1 + u]);
+            if constexpr (!PC::REAL) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bfree)) : "memory");
+                stage_math<T, E, R1, R0, INV, TW_LUT>(v, lutB, p.table, 0, j1);
+                cf* ocol = p.out + prob * N + c0 + g1;
+                static_for<0, B1>([&](auto q_) {
+                    constexpr int q = decltype(q_)::value;
+                    const int jq = j1 + q * T;
+                    static_for<0, R1>([&](auto u_) {
+                        constexpr int u = decltype(u_)::value;
+                        __stcs(ocol + (long long) (jq + u * STR1) * L0, v[q * R1 + u]);
+                    });
                 });
-            });
+            } else {
+                // real forward.  Bin k = col + L0*row pairs with M - k = (L0 - col) + L0*(L - 1 - row): partner slot,
+                // mirrored row.  A thread's rows u < R1/2 are bins below M/2, the others above: the upper half of Z goes
+                // through the tile buffer ([slot][row], odd pitch), every thread then evaluates its lower-half bins
+                // together with their mirrors -- each pair once, with the arithmetic of the separate split pass
+                // (four_step.cuh real_split_kernel) -- and stores Y[k] and Y[M-k].
+                consumer_sync();                               // every thread has gathered: the buffer can be rewritten
+                stage_math<T, E, R1, R0, INV, TW_LUT>(v, lutB, p.table, 0, j1);
+                constexpr int ZP = L + 1;
+                constexpr int H = C / 2;
+                static_assert(R1 % 2 == 0, "the last radix splits into a lower and an upper half");
+                static_for<0, B1>([&](auto q_) {
+                    constexpr int q = decltype(q_)::value;
+                    static_for<R1 / 2, R1>([&](auto u_) {
+                        constexpr int u = decltype(u_)::value;
+                        xb[g1 * ZP + j1 + q * T + u * STR1] = v[q * R1 + u];
+                    });
+                });
+                consumer_sync();
+                const int col = pass2_column(c0, g1);
+                const bool self0 = col == 0, selfh = col == L0 / 2;
+                const int gm = (self0 || selfh) ? g1 : (g1 ^ H);              // partner slot
+                constexpr long long M = N;
+                cf* yrow = p.out + prob * p.out_stride;
+                static_for<0, B1>([&](auto q_) {
+                    constexpr int q = decltype(q_)::value;
+                    static_for<0, R1 / 2>([&](auto u_) {
+                        constexpr int u = decltype(u_)::value;
+                        const int kr = j1 + q * T + u * STR1;                  // row < L/2: bin k = col + L0 * kr < M/2
+                        const int km = self0 ? (L - kr) : (L - 1 - kr);
+                        const cf z0 = v[q * R1 + u];
+                        const cf z1 = (self0 && kr == 0) ? z0 : xb[gm * ZP + km];
+                        const unsigned k = (unsigned) col + (unsigned) L0 * (unsigned) kr;
+                        const unsigned e = k << p.tw_shift_real;
+                        const cf w = cmul(__ldg(p.tw_lo + (e & ((1u << p.tw_h) - 1u))), __ldg(p.tw_hi + (e >> p.tw_h)));
+                        const cf sum = make_float2(z0.x + z1.x, z0.y - z1.y);
+                        const cf dif = make_float2(z0.x - z1.x, z0.y + z1.y);
+                        const cf cc = cmul(make_float2(-w.y, w.x), dif);
+                        __stcs(yrow + k, make_float2(sum.x - cc.x, sum.y - cc.y));
+                        __stcs(yrow + (M - k), make_float2(sum.x + cc.x, -(sum.y + cc.y)));
+                    });
+                });
+                if (self0 && j1 == 0) {                                        // bin M/2 (column 0, row L/2) mirrors itself
+                    const cf m = v[R1 / 2];
+                    __stcs(yrow + M / 2, make_float2(2.0f * m.x, -2.0f * m.y));
+                }
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bfree)) : "memory");
+            }
         }
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_stored)) : "memory");
     }

@@ -135,6 +135,38 @@ def test_pipelined_two_pass_matches_two_kernel_path(log2n, batch):
                 assert rel_rms(y[b].cpu().numpy(), oracle.fp64_c2c(x[b].cpu().numpy(), inverse)) <= tolerance(n)
 
 
+@pytest.mark.parametrize("log2n,batch", [(16, 130), (17, 70), (18, 40), (19, 24), (20, 12), (21, 6)])
+def test_pipelined_real_forward_fused_split(log2n, batch):
+    """Real forward transforms above the single-pass limit: the split runs inside pass 2 of the dataflow kernel
+    (mirror-paired tile columns).  Checked against the oracle, fp64, and the separate split pass."""
+    import os
+
+    n = 1 << log2n
+    rng = np.random.default_rng(log2n)
+    x = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    with ck.Context(n, ck.BOTH) as ctx:
+        os.environ["CKFFT_B200_PIPE_REAL"] = "1"
+        try:
+            for rep in range(2):
+                y = ctx.real_forward(xd)
+            torch.cuda.synchronize()
+            os.environ["CKFFT_B200_PIPE_REAL"] = "0"
+            y0 = ctx.real_forward(xd)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("CKFFT_B200_PIPE_REAL", None)
+        assert y.shape == (batch, n // 2 + 1)
+        assert rel_rms(y.cpu().numpy(), y0.cpu().numpy()) <= 1e-7
+        orc = oracle.Restatement(n, 3)
+        for b in (0, batch // 2, batch - 1):
+            got = y[b].cpu().numpy()
+            assert rel_rms(got, orc.real_forward(x[b:b + 1])[0]) <= tolerance(n)
+            assert rel_rms(got, oracle.fp64_real_forward(x[b:b + 1])[0]) <= tolerance(n)
+            assert got[0].imag == 0.0 and got[-1].imag == 0.0          # DC and Nyquist bins are real
+        orc.close()
+
+
 @pytest.mark.parametrize("log2n", [16, 17, 20, 22])
 def test_large_real_vs_oracle(log2n):
     n = 1 << log2n
