@@ -18,6 +18,7 @@ B200_SYMBOLS = ["CkFftComplexForwardBatch", "CkFftComplexInverseBatch", "CkFftRe
                 "CkFftB200LastError", "CkFftB200KernelLaunches", "CkFftB200HostAlloc", "CkFftB200HostFree",
                 "CkFftB200ContextDevice", "CkFftB200PackColumnsAsync", "CkFftB200UnpackTransposeAsync",
                 "CkFftB200TwiddleRowsAsync", "CkFftB200RealForwardPowerBatchAsync",
+                "CkFftB200ComplexForwardPlanarBatchAsync", "CkFftB200ComplexInversePlanarBatchAsync",
                 "CkFftB200DistGetLayout", "CkFftB200DistDescribe", "CkFftB200PeerAlloc", "CkFftB200PeerFree",
                 "CkFftB200PeerExport", "CkFftB200PeerOpen", "CkFftB200PeerClose", "CkFftB200DistPlanCreate",
                 "CkFftB200DistExecAsync", "CkFftB200DistPlanStatus", "CkFftB200DistPlanDestroy",
@@ -85,6 +86,8 @@ def load() -> C.CDLL:
     lib.CkFftB200UnpackTransposeAsync.argtypes = [vp, vp, i, sz, sz, vp]
     lib.CkFftB200TwiddleRowsAsync.argtypes = [vp, i, vp, sz, sz, sz, i, vp]
     lib.CkFftB200RealForwardPowerBatchAsync.argtypes = [vp, i, vp, vp, vp, sz, sz, sz, vp]
+    for name in ("CkFftB200ComplexForwardPlanarBatchAsync", "CkFftB200ComplexInversePlanarBatchAsync"):
+        getattr(lib, name).argtypes = [vp, i, vp, vp, vp, vp, sz, sz, sz, vp]
     lib.CkFftB200DistGetLayout.argtypes = [C.c_longlong, i, i, C.POINTER(DistLayout)]
     lib.CkFftB200DistDescribe.argtypes = [C.POINTER(DistLayout), i, C.POINTER(DistPass)]
     lib.CkFftB200PeerAlloc.restype = vp

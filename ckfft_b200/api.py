@@ -140,6 +140,25 @@ class Context:
             out = self._empty_like(x, tuple(x.shape), np.complex64, "complex64")
         return self._run(name, n, x, out, batch)
 
+    def complex_planar(self, re, im, inverse: bool = False, out=None):
+        """Split-complex transform (CkFftB200Complex{Forward,Inverse}PlanarBatchAsync): re, im float32[..., n] CUDA
+        tensors -> (re, im) of the spectrum.  `out=(re, im)` transforms in place.  Stream-ordered on torch's stream."""
+        import torch
+
+        re = self._prep(re, np.float32, "float32")
+        im = self._prep(im, np.float32, "float32")
+        if not _is_torch(re) or not _is_torch(im) or re.shape != im.shape:
+            raise CkFftError("complex_planar works on two CUDA tensors of the same shape")
+        n = re.shape[-1]
+        batch = int(np.prod(re.shape[:-1], dtype=np.int64)) if re.ndim > 1 else 1
+        if out is None:
+            out = (torch.empty_like(re), torch.empty_like(im))
+        fn = self._lib.CkFftB200ComplexInversePlanarBatchAsync if inverse else self._lib.CkFftB200ComplexForwardPlanarBatchAsync
+        stream = torch.cuda.current_stream(re.device).cuda_stream
+        if not fn(self._ctx, n, re.data_ptr(), im.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), batch, 0, 0, stream):
+            self._fail("CkFftB200ComplexPlanarBatchAsync")
+        return out
+
     def real_forward(self, x, out=None):
         """CkFftRealForward: float32[..., n] -> complex64[..., n/2+1] (= 2 * rfft)."""
         x = self._prep(x, np.float32, "float32")

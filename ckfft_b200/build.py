@@ -40,6 +40,8 @@ UNITS = [
     ("r2c.o", "fft_variants.cu", ["-DCKB_VARIANT=2"]),
     ("c2r.o", "fft_variants.cu", ["-DCKB_VARIANT=3"]),
     ("r2c_audio.o", "fft_variants.cu", ["-DCKB_VARIANT=4"]),
+    ("c2c_fwd_planar.o", "fft_variants.cu", ["-DCKB_VARIANT=5"]),
+    ("c2c_inv_planar.o", "fft_variants.cu", ["-DCKB_VARIANT=6"]),
 ]
 
 

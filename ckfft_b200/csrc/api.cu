@@ -233,13 +233,13 @@ cudaError_t enqueue(const _CkFftContext* c, Kind kind, int n, const void* in, vo
 }
 
 // the reference's checks for one transform call (src/ckfft/ckfft.cpp:36-114), plus count <= 0
-bool check_call(const _CkFftContext* c, Kind kind, int n, const void* in, const void* out)
+bool check_call(const _CkFftContext* c, Kind kind, int n, const void* in, const void* out, bool allow_inplace = false)
 {
     if (!c || c->magic != kMagic) { set_error("invalid context"); return false; }
     const bool needs_inv = (kind == K_C2C_INV || kind == K_C2R);
     if (needs_inv ? !c->invExpTable : !c->fwdExpTable) { set_error("context was not created for this direction"); return false; }
     if (!is_pow2(n) || n > c->maxCount) { set_error("n must be a power of two <= nMax"); return false; }
-    if (!in || !out || in == out) { set_error("input/output must be distinct non-NULL buffers"); return false; }
+    if (!in || !out || (in == out && !allow_inplace)) { set_error("input/output must be distinct non-NULL buffers"); return false; }
     return true;
 }
 
@@ -433,15 +433,31 @@ int run_sync(CkFftContext* c, Kind kind, int n, const void* in, void* out, size_
     return 1;
 }
 
+// In-place rule of the stream-ordered calls: `input == output` is accepted when every transform
+// reads and writes the same bytes -- complex: equal strides; real: the real-array stride is twice the spectrum
+// stride (rows padded to n + 2 floats, the usual in-place real layout).  Every kernel reads a whole row (tile) into
+// registers / shared memory before it stores any of it, and the multi-pass paths write `output` only after the
+// pass that reads `input` has consumed that transform, so such calls are safe.  Partial overlap stays undefined.
+bool inplace_strides_ok(Kind kind, size_t in_stride, size_t out_stride)
+{
+    if (kind == K_R2C) return in_stride == 2 * out_stride;
+    if (kind == K_C2R) return out_stride == 2 * in_stride;
+    return in_stride == out_stride;
+}
+
 int run_async(CkFftContext* c, Kind kind, int n, const void* in, void* out, size_t batch, size_t in_stride,
               size_t out_stride, void* stream)
 {
-    if (!check_call(c, kind, n, in, out)) return 0;
+    if (!check_call(c, kind, n, in, out, true)) return 0;
     if (batch == 0) return 1;
     if (!supported_size(c, kind, n)) { set_error("transform length not supported by this build"); return 0; }
     if (in_stride == 0) in_stride = in_elems(kind, n);
     if (out_stride == 0) out_stride = out_elems(kind, n);
     if (in_stride < in_elems(kind, n) || out_stride < out_elems(kind, n)) { set_error("stride shorter than one transform"); return 0; }
+    if (in == out && !inplace_strides_ok(kind, in_stride, out_stride)) {
+        set_error("in-place call: input and output rows must coincide (complex: equal strides; real: real stride = 2 x spectrum stride)");
+        return 0;
+    }
     if (((uintptr_t) in | (uintptr_t) out) & 7) { set_error("device pointers must be 8-byte aligned"); return 0; }
     if ((kind == K_R2C && n > 16 && (in_stride & 1)) || (kind == K_C2R && n > 16 && (out_stride & 1))) {
         set_error("real-array strides must be even");
@@ -746,6 +762,49 @@ void CkFftB200HostFree(void* p)
 }
 
 int CkFftB200ContextDevice(const CkFftContext* c) { return (c && c->magic == kMagic) ? c->device : -1; }
+
+// ---- split-complex ("planar") arrays: re[] and im[] separate, strides in floats ----
+static int run_planar(CkFftContext* c, bool inverse, int n, const float* inRe, const float* inIm, float* outRe, float* outIm,
+                      size_t batch, size_t inStride, size_t outStride, void* stream)
+{
+    const Kind kind = inverse ? K_C2C_INV : K_C2C_FWD;
+    if (!check_call(c, kind, n, inRe, outRe, true)) return 0;
+    if (!inIm || !outIm) { set_error("planar: NULL imaginary array"); return 0; }
+    if (n > CKB_MAX_SINGLE_PASS) { set_error("planar: n must be <= 16384"); return 0; }
+    if (batch == 0) return 1;
+    if (inStride == 0) inStride = (size_t) n;
+    if (outStride == 0) outStride = (size_t) n;
+    if (inStride < (size_t) n || outStride < (size_t) n) { set_error("stride shorter than one transform"); return 0; }
+    if (((uintptr_t) inRe | (uintptr_t) inIm | (uintptr_t) outRe | (uintptr_t) outIm) & 3) { set_error("planar: misaligned pointer"); return 0; }
+    // in place = both planes onto themselves with equal strides; any other aliasing between the four arrays is rejected
+    const bool inplace = inRe == outRe && inIm == outIm;
+    if (inplace ? inStride != outStride : (inRe == outRe || inIm == outIm || (const float*) outRe == inIm || (const float*) outIm == inRe)) {
+        set_error("planar: arrays must be distinct, or both planes transformed in place with equal strides");
+        return 0;
+    }
+    if (inRe == inIm || outRe == outIm) { set_error("planar: real and imaginary arrays must be distinct"); return 0; }
+    DeviceGuard guard(c->device);
+    if (!guard.ok) { set_error("cannot select the context's device"); return 0; }
+    ckb::KernelParams p{ (const ckb::cf*) inRe, (ckb::cf*) outRe, c->dTable, c->log2Table, (long long) batch,
+                         (long long) inStride, (long long) outStride, nullptr, inIm, outIm };
+    cudaError_t e;
+    if (n <= 8) e = ckb::launch_tiny_c2c(n, inverse, p, (cudaStream_t) stream);
+    else        e = inverse ? ckb::launch_c2c_inv_planar(n, p, (cudaStream_t) stream) : ckb::launch_c2c_fwd_planar(n, p, (cudaStream_t) stream);
+    if (e != cudaSuccess) { set_error("kernel launch", e); return 0; }
+    return 1;
+}
+
+int CkFftB200ComplexForwardPlanarBatchAsync(CkFftContext* c, int n, const float* inRe, const float* inIm, float* outRe, float* outIm,
+                                            size_t batch, size_t inStride, size_t outStride, void* stream)
+{
+    return run_planar(c, false, n, inRe, inIm, outRe, outIm, batch, inStride, outStride, stream);
+}
+
+int CkFftB200ComplexInversePlanarBatchAsync(CkFftContext* c, int n, const float* inRe, const float* inIm, float* outRe, float* outIm,
+                                            size_t batch, size_t inStride, size_t outStride, void* stream)
+{
+    return run_planar(c, true, n, inRe, inIm, outRe, outIm, batch, inStride, outStride, stream);
+}
 
 // ---- audio front end: window, real forward transform and power spectrum in one kernel ----
 int CkFftB200RealForwardPowerBatchAsync(CkFftContext* c, int n, const float* in, const float* window, float* power,

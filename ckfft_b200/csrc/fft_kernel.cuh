@@ -45,6 +45,10 @@ struct KernelParams {
     long long in_stride;   // distance between consecutive transforms, in 8-byte units
     long long out_stride;  // (AUDIO kernels: the output is a float array and this stride is in floats)
     const cf* window;      // AUDIO kernels: analysis window, n floats viewed as M complex, or nullptr
+    // PLANAR kernels (split-complex layout): `in` / `out` are the arrays of real parts viewed as
+    // float*, these the arrays of imaginary parts; both strides are in floats
+    const float* in_im;
+    float* out_im;
 };
 
 template <int LOGPAD> __device__ __forceinline__ int padidx(int p) { return p + (p >> LOGPAD); }
@@ -281,6 +285,36 @@ __device__ __forceinline__ void stage_scatter(const cf (&v)[E], cf* __restrict__
     });
 }
 
+// Split-complex ("planar") rows: real and imaginary parts live in two float arrays.  A warp request is then a run of
+// contiguous 4-byte elements (128 B per array for T >= 32), still whole sectors; same butterfly maps as above.
+template <int M, int T, int E, int R>
+__device__ __forceinline__ void gather_planar(cf (&v)[E], const float* __restrict__ re, const float* __restrict__ im, int j, bool valid)
+{
+    constexpr int B = E / R, STR = M / R;
+    static_for<0, B>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        const int jq = j + q * T;
+        static_for<0, R>([&](auto t_) {
+            constexpr int t = decltype(t_)::value;
+            if (valid) v[q * R + bitrev<R>(t)] = make_float2(__ldcs(re + jq + t * STR), __ldcs(im + jq + t * STR));
+        });
+    });
+}
+
+template <int M, int T, int E, int R>
+__device__ __forceinline__ void scatter_planar(const cf (&v)[E], float* __restrict__ re, float* __restrict__ im, int j, bool valid)
+{
+    constexpr int B = E / R, STR = M / R;
+    static_for<0, B>([&](auto q_) {
+        constexpr int q = decltype(q_)::value;
+        const int jq = j + q * T;
+        static_for<0, R>([&](auto u_) {
+            constexpr int u = decltype(u_)::value;
+            if (valid) { __stcs(re + jq + u * STR, v[q * R + u].x); __stcs(im + jq + u * STR, v[q * R + u].y); }
+        });
+    });
+}
+
 // Where a real-forward kernel puts bin k: the complex value, or -- AUDIO kernels (what an audio caller
 // of CkFftRealForward does next) -- its squared magnitude into a float array, which halves the bytes written.
 template <bool AUDIO>
@@ -374,8 +408,10 @@ __device__ __forceinline__ void gather_rows(cf (&v)[E], const cf* __restrict__ c
 enum Prefetch { PF_NONE = 0, PF_DOUBLE = 1, PF_INPLACE = 2, PF_SPLIT = 3 };
 
 template <int M_, int E_, int R0_, int R1_, int R2_, int G_, bool INV_, int MODE_, int MINB_ = 1, int PF_ = PF_NONE, bool TWR_ = false,
-          bool AUDIO_ = false>
+          bool AUDIO_ = false, bool PLANAR_ = false>
 struct Cfg {
+    static constexpr bool PLANAR = PLANAR_;   // split-complex input and output (complex transforms, plain loads)
+    static_assert(!PLANAR_ || (MODE_ == MODE_C2C && PF_ == PF_NONE), "planar rows: complex transforms without bulk prefetch");
     static constexpr bool AUDIO = AUDIO_;   // real forward with a fused analysis window (load) and power spectrum (store)
     static_assert(!AUDIO_ || MODE_ == MODE_R2C, "the audio front end is a real-forward kernel");
     static constexpr int PF = PF_;
@@ -563,6 +599,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             stage_gather<M, T, E, R0, LOGPAD, SRC_INBUF>(v, src, inb, j, valid);
             group_sync<T>(g);                      // every thread of the group has drained the staging buffer
             if constexpr (C::PF == PF_DOUBLE) issue_next(item);
+        } else if constexpr (C::PLANAR) {
+            gather_planar<M, T, E, R0>(v, reinterpret_cast<const float*>(p.in) + item * p.in_stride, p.in_im + item * p.in_stride, j, valid);
         } else {
             stage_gather<M, T, E, R0, LOGPAD, SRC_GLOBAL>(v, src, xb, j, valid);
         }
@@ -593,6 +631,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             } else if constexpr (MODE == MODE_R2C) {
                 group_sync<T>(g);
                 stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XNAT>(v, dst, xb, j, valid);
+            } else if constexpr (C::PLANAR) {
+                scatter_planar<M, T, E, R1>(v, reinterpret_cast<float*>(p.out) + item * p.out_stride, p.out_im + item * p.out_stride, j, valid);
             } else {
                 stage_scatter<M, T, E, R1, R0, LOGPAD, DST_GLOBAL>(v, dst, xb, j, valid);
             }
@@ -611,6 +651,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             } else if constexpr (MODE == MODE_R2C) {
                 group_sync<T>(g);
                 stage_scatter<M, T, E, R2, R0 * R1, LOGPAD, DST_XNAT>(v, dst, xb, j, valid);
+            } else if constexpr (C::PLANAR) {
+                scatter_planar<M, T, E, R2>(v, reinterpret_cast<float*>(p.out) + item * p.out_stride, p.out_im + item * p.out_stride, j, valid);
             } else {
                 stage_scatter<M, T, E, R2, R0 * R1, LOGPAD, DST_GLOBAL>(v, dst, xb, j, valid);
             }

@@ -1,17 +1,19 @@
 // fft_variants.cu -- instantiates the single-pass kernel family for ONE (direction, mode) variant.
-// Compiled five times (-DCKB_VARIANT=0..4) so the heavy template instantiations build in parallel:
+// Compiled seven times (-DCKB_VARIANT=0..6) so the heavy template instantiations build in parallel:
 //   0  complex forward   (CkFftComplexForward,  reference src/ckfft/ckfft.cpp:78-95)
 //   1  complex inverse   (CkFftComplexInverse,  :97-114)
 //   2  real forward      (CkFftRealForward,     :36-53)   half-length forward FFT + fused split
 //   3  real inverse      (CkFftRealInverse,     :55-76)   fused twist + half-length inverse FFT
 //   4  audio front end   (no reference counterpart) window * frame -> real forward -> |Y|^2
+//   5  complex forward, split-complex ("planar") arrays   (callers that hold re[] / im[] separately)
+//   6  complex inverse, split-complex arrays
 #include "launch.h"
 #include "plans.h"
 #include <stdint.h>
 #include <stdlib.h>
 
 #ifndef CKB_VARIANT
-#error "compile with -DCKB_VARIANT=0..4"
+#error "compile with -DCKB_VARIANT=0..6"
 #endif
 
 namespace ckb {
@@ -28,11 +30,18 @@ static constexpr bool kInv = false; static constexpr int kMode = MODE_R2C;
 #elif CKB_VARIANT == 3
 #define CKB_FN launch_c2r
 static constexpr bool kInv = true; static constexpr int kMode = MODE_C2R;
-#else
+#elif CKB_VARIANT == 4
 #define CKB_FN launch_r2c_audio
 static constexpr bool kInv = false; static constexpr int kMode = MODE_R2C;
+#elif CKB_VARIANT == 5
+#define CKB_FN launch_c2c_fwd_planar
+static constexpr bool kInv = false; static constexpr int kMode = MODE_C2C;
+#else
+#define CKB_FN launch_c2c_inv_planar
+static constexpr bool kInv = true; static constexpr int kMode = MODE_C2C;
 #endif
 static constexpr bool kAudio = CKB_VARIANT == 4;
+static constexpr bool kPlanar = CKB_VARIANT >= 5;
 
 static int prefetch_mode()
 {
@@ -74,7 +83,7 @@ static cudaError_t launch_cfg(const KernelParams& p, cudaStream_t s)
 
 cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
 {
-#if CKB_VARIANT != 3
+#if CKB_VARIANT != 3 && CKB_VARIANT < 5
     // bulk copies need 16-byte aligned rows
     if (prefetch_mode() && ((uintptr_t) p.in & 15) == 0 && (p.in_stride & 1) == 0) {
         switch (M) {
@@ -151,7 +160,7 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
 #endif
     switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0, kAudio>>(p, s);
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0, kAudio, kPlanar>>(p, s);
         CKB_SINGLE_PASS_PLANS(X)
 #undef X
         default: return cudaErrorInvalidValue;

@@ -8,12 +8,14 @@ struct CUtensorMap_st;                 // <cuda.h>; only pointers to it cross th
 
 namespace ckb {
 
-// one variant per translation unit (fft_variants.cu is compiled four times)
+// one variant per translation unit (fft_variants.cu is compiled once per variant)
 cudaError_t launch_c2c_fwd(int M, const KernelParams& p, cudaStream_t s);
 cudaError_t launch_c2c_inv(int M, const KernelParams& p, cudaStream_t s);
 cudaError_t launch_r2c(int M, const KernelParams& p, cudaStream_t s);
 cudaError_t launch_c2r(int M, const KernelParams& p, cudaStream_t s);
 cudaError_t launch_r2c_audio(int M, const KernelParams& p, cudaStream_t s);   // window + real forward + power spectrum
+cudaError_t launch_c2c_fwd_planar(int M, const KernelParams& p, cudaStream_t s);   // split-complex arrays (p.in_im / p.out_im)
+cudaError_t launch_c2c_inv_planar(int M, const KernelParams& p, cudaStream_t s);
 
 // tiny sizes (tiny.cu)
 cudaError_t launch_tiny_c2c(int n, bool inverse, const KernelParams& p, cudaStream_t s);

@@ -16,8 +16,13 @@ static int tiny_grid(long long batch)
 template <int M>
 static cudaError_t tiny_c2c(bool inverse, const KernelParams& p, cudaStream_t s)
 {
-    if (inverse) tiny_c2c_kernel<M, true><<<tiny_grid(p.batch), 128, 0, s>>>(p);
-    else         tiny_c2c_kernel<M, false><<<tiny_grid(p.batch), 128, 0, s>>>(p);
+    if (p.in_im != nullptr) {           // split-complex rows
+        if (inverse) tiny_c2c_kernel<M, true, true><<<tiny_grid(p.batch), 128, 0, s>>>(p);
+        else         tiny_c2c_kernel<M, false, true><<<tiny_grid(p.batch), 128, 0, s>>>(p);
+    } else {
+        if (inverse) tiny_c2c_kernel<M, true><<<tiny_grid(p.batch), 128, 0, s>>>(p);
+        else         tiny_c2c_kernel<M, false><<<tiny_grid(p.batch), 128, 0, s>>>(p);
+    }
     count_launch();
     return cudaGetLastError();
 }

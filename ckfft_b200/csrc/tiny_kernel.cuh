@@ -7,23 +7,34 @@
 
 namespace ckb {
 
-template <int M, bool INV>
+template <int M, bool INV, bool PLANAR = false>
 __global__ void __launch_bounds__(128) tiny_c2c_kernel(const KernelParams p)
 {
     for (long long item = blockIdx.x * (long long) blockDim.x + threadIdx.x; item < p.batch;
          item += (long long) gridDim.x * blockDim.x) {
-        const cf* src = p.in + item * p.in_stride;
-        cf* dst = p.out + item * p.out_stride;
         cf v[M];
-        static_for<0, M>([&](auto t_) { constexpr int t = decltype(t_)::value; v[bitrev<M>(t)] = src[t]; });
-        fft_regs<M, 0, INV>(v);
-        static_for<0, M>([&](auto u_) { constexpr int u = decltype(u_)::value; dst[u] = v[u]; });
+        if constexpr (PLANAR) {
+            // split-complex rows (strides in floats)
+            const float* re = reinterpret_cast<const float*>(p.in) + item * p.in_stride;
+            const float* im = p.in_im + item * p.in_stride;
+            static_for<0, M>([&](auto t_) { constexpr int t = decltype(t_)::value; v[bitrev<M>(t)] = make_float2(re[t], im[t]); });
+            fft_regs<M, 0, INV>(v);
+            float* ore = reinterpret_cast<float*>(p.out) + item * p.out_stride;
+            float* oim = p.out_im + item * p.out_stride;
+            static_for<0, M>([&](auto u_) { constexpr int u = decltype(u_)::value; ore[u] = v[u].x; oim[u] = v[u].y; });
+        } else {
+            const cf* src = p.in + item * p.in_stride;
+            cf* dst = p.out + item * p.out_stride;
+            static_for<0, M>([&](auto t_) { constexpr int t = decltype(t_)::value; v[bitrev<M>(t)] = src[t]; });
+            fft_regs<M, 0, INV>(v);
+            static_for<0, M>([&](auto u_) { constexpr int u = decltype(u_)::value; dst[u] = v[u]; });
+        }
     }
 }
 
 // real forward, n = N floats -> N/2+1 complex.  Strides in floats (input) / complex (output).
 template <int N>
-__global__ void __launch_bounds__(128) tiny_r2c_kernel(const float* __restrict__ in, cf* __restrict__ out,
+__global__ void __launch_bounds__(128) tiny_r2c_kernel(const float* in, cf* out,       // may alias (in-place calls)
                                                        const cf* __restrict__ table, int log2_nt, long long batch,
                                                        long long in_stride, long long out_stride)
 {
@@ -34,8 +45,9 @@ __global__ void __launch_bounds__(128) tiny_r2c_kernel(const float* __restrict__
         if constexpr (N == 1) {
             y[0] = make_float2(x[0] * 2.0f, 0.0f);
         } else if constexpr (N == 2) {
-            y[0] = make_float2((x[0] + x[1]) * 2.0f, 0.0f);
-            y[1] = make_float2((x[0] - x[1]) * 2.0f, 0.0f);
+            const float x0 = x[0], x1 = x[1];
+            y[0] = make_float2((x0 + x1) * 2.0f, 0.0f);
+            y[1] = make_float2((x0 - x1) * 2.0f, 0.0f);
         } else if constexpr (N == 4) {
             const float s02 = (x[0] + x[2]) * 2.0f, d02 = (x[0] - x[2]) * 2.0f;
             const float s13 = (x[1] + x[3]) * 2.0f, d13 = (x[1] - x[3]) * 2.0f;
@@ -68,7 +80,7 @@ __global__ void __launch_bounds__(128) tiny_r2c_kernel(const float* __restrict__
 
 // real inverse, N/2+1 complex -> N floats.  Strides in complex (input) / floats (output).
 template <int N>
-__global__ void __launch_bounds__(128) tiny_c2r_kernel(const cf* __restrict__ in, float* __restrict__ out,
+__global__ void __launch_bounds__(128) tiny_c2r_kernel(const cf* in, float* out,       // may alias (in-place calls)
                                                        const cf* __restrict__ table, int log2_nt, long long batch,
                                                        long long in_stride, long long out_stride)
 {
@@ -79,8 +91,9 @@ __global__ void __launch_bounds__(128) tiny_c2r_kernel(const cf* __restrict__ in
         if constexpr (N == 1) {
             x[0] = y[0].x;
         } else if constexpr (N == 2) {
-            x[0] = y[0].x + y[1].x;
-            x[1] = y[0].x - y[1].x;
+            const float y0 = y[0].x, y1 = y[1].x;
+            x[0] = y0 + y1;
+            x[1] = y0 - y1;
         } else if constexpr (N == 4) {
             const float s02 = y[0].x + y[2].x, s13 = 2.0f * y[1].x;
             const float d02 = y[0].x - y[2].x, d13 = 2.0f * y[1].y;

@@ -37,6 +37,12 @@ int CkFftRealInverseBatch(CkFftContext* context, int n, const CkFftComplex* inpu
  * Strides are in elements of the respective array (complex elements or floats); 0 selects the
  * dense default.  Real-array strides must be even and all pointers 8-byte aligned.
  * Returns 1 if the work was enqueued, 0 on invalid arguments or a CUDA error.
+ *
+ * In place: unlike the classic calls (which keep the reference's `input == output -> 0`, src/ckfft/ckfft.cpp:46,69,
+ * 88,107), these accept input == output when every transform reads and writes the same bytes: complex transforms
+ * with inStride == outStride; real transforms with the real-array stride equal to twice the spectrum stride (rows
+ * padded to n + 2 floats).  Real transforms longer than 32768 points and partially overlapping arrays are not
+ * supported in place.
  */
 int CkFftComplexForwardBatchAsync(CkFftContext* context, int n, const CkFftComplex* input, CkFftComplex* output,
                                   size_t batch, size_t inStride, size_t outStride, void* stream);
@@ -46,6 +52,20 @@ int CkFftRealForwardBatchAsync(CkFftContext* context, int n, const float* input,
                                size_t batch, size_t inStride, size_t outStride, void* stream);
 int CkFftRealInverseBatchAsync(CkFftContext* context, int n, const CkFftComplex* input, float* output,
                                size_t batch, size_t inStride, size_t outStride, void* stream);
+
+/*
+ * Split-complex ("planar") arrays: real and imaginary parts in two float arrays, as vDSP-style callers hold them
+ * (the layout of the reference harness's Accelerate competitor, DSPSplitComplex, src/test/test.cpp:398-461).  Same
+ * transform, scaling and checks as CkFftComplexForward / CkFftComplexInverse; n <= 16384, device pointers (4-byte
+ * aligned), stream-ordered; strides in floats (0 = n).  In place (outRe == inRe and outIm == inIm, equal strides)
+ * is accepted; any other aliasing between the four arrays returns 0.
+ */
+int CkFftB200ComplexForwardPlanarBatchAsync(CkFftContext* context, int n, const float* inRe, const float* inIm,
+                                            float* outRe, float* outIm, size_t batch, size_t inStride, size_t outStride,
+                                            void* stream);
+int CkFftB200ComplexInversePlanarBatchAsync(CkFftContext* context, int n, const float* inRe, const float* inIm,
+                                            float* outRe, float* outIm, size_t batch, size_t inStride, size_t outStride,
+                                            void* stream);
 
 /*
  * Audio front end: what a caller of CkFftRealForward on audio frames does next, fused into the transform kernel.

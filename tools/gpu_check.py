@@ -65,8 +65,23 @@ def sweep(sizes, total_log2=27, iters=10):
         x = torch.empty((batch, n), dtype=torch.complex64, device="cuda")
         x.real.uniform_(-1, 1); x.imag.uniform_(-1, 1)
         out = torch.empty_like(x)
-        for kind in ("c2c", "r2c", "c2r"):
-            if kind == "c2c":
+        kinds = ("c2c", "r2c", "c2r") + (("c2cp", "c2ci") if os.environ.get("CKFFT_SWEEP_LAYOUTS") and n <= 16384 else ())
+        for kind in kinds:
+            if kind == "c2cp":          # split-complex arrays
+                xre = x.view(torch.float32).view(-1)[: batch * n].view(batch, n)
+                xim = x.view(torch.float32).view(-1)[batch * n:].view(batch, n)
+                ore = out.view(torch.float32).view(-1)[: batch * n].view(batch, n)
+                oim = out.view(torch.float32).view(-1)[batch * n:].view(batch, n)
+                f = lambda: ctx.complex_planar(xre, xim, False, (ore, oim))
+                nbytes = 16 * n * batch
+                flops = 5 * n * np.log2(n) * batch
+            elif kind == "c2ci":        # in place
+                lib = ck._lib.load()
+                f = lambda: lib.CkFftComplexForwardBatchAsync(ctx.handle, n, out.data_ptr(), out.data_ptr(), batch, 0, 0,
+                                                              torch.cuda.current_stream().cuda_stream)
+                nbytes = 16 * n * batch
+                flops = 5 * n * np.log2(n) * batch
+            elif kind == "c2c":
                 f = lambda: ctx.complex_forward(x, out)
                 nbytes = 16 * n * batch
                 flops = 5 * n * np.log2(n) * batch
