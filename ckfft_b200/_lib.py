@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "libckfft_b200.so")
+LIB_PATH = os.environ.get("CKFFT_B200_LIB") or os.path.join(PKG, "lib", "libckfft_b200.so")   # override: A/B builds (build.py)
 
 # every symbol the two public headers declare (tests check the .so exports exactly these)
 CLASSIC_SYMBOLS = ["CkFftInit", "CkFftRealForward", "CkFftRealInverse", "CkFftComplexForward",

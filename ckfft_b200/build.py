@@ -20,8 +20,11 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-OBJ = os.path.join(PKG, "build")
-LIB = os.path.join(PKG, "lib", "libckfft_b200.so")
+# CKFFT_B200_BUILD_TAG=<tag> (development): objects in build_<tag>/, library lib/libckfft_b200_<tag>.so, so that an A/B
+# build (CKFFT_B200_NVCC_FLAGS="-D...") sits next to the product library; CKFFT_B200_LIB=<path> makes _lib.py load it.
+_TAG = os.environ.get("CKFFT_B200_BUILD_TAG", "")
+OBJ = os.path.join(PKG, "build" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(PKG, "lib", "libckfft_b200" + ("_" + _TAG if _TAG else "") + ".so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
