@@ -411,7 +411,7 @@ template <int M_, int E_, int R0_, int R1_, int R2_, int G_, bool INV_, int MODE
           bool AUDIO_ = false, bool PLANAR_ = false>
 struct Cfg {
     static constexpr bool PLANAR = PLANAR_;   // split-complex input and output (complex transforms, plain loads)
-    static_assert(!PLANAR_ || (MODE_ == MODE_C2C && PF_ == PF_NONE), "planar rows: complex transforms without bulk prefetch");
+    static_assert(!PLANAR_ || (MODE_ == MODE_C2C && (PF_ == PF_NONE || PF_ == PF_INPLACE || PF_ == PF_SPLIT)), "planar rows: complex transforms");
     static constexpr bool AUDIO = AUDIO_;   // real forward with a fused analysis window (load) and power spectrum (store)
     static_assert(!AUDIO_ || MODE_ == MODE_R2C, "the audio front end is a real-forward kernel");
     static constexpr int PF = PF_;
@@ -506,6 +506,16 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
     // last row whose over-copy would leave the array out of this kernel.
     constexpr unsigned kCopyBytes = (MODE == MODE_C2R ? M + 2 : M) * 8;
     auto issue_row = [&](long long row) {
+        if constexpr (C::PLANAR) {
+            // split-complex rows: two copies, the real parts into floats [0, M) of the buffer, the imaginary parts behind them
+            if (j == 0 && row < p.batch) {
+                float* fb = reinterpret_cast<float*>(inb);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(mbar, M * 8);
+                bulk_load(fb, reinterpret_cast<const float*>(p.in) + row * p.in_stride, M * 4, mbar, l2pol);
+                bulk_load(fb + M, p.in_im + row * p.in_stride, M * 4, mbar, l2pol);
+            }
+        } else
         if (j == 0 && row < p.batch) {
             const cf* rsrc = p.in + row * p.in_stride;
             if constexpr (MODE == MODE_C2R) rsrc = reinterpret_cast<const cf*>(reinterpret_cast<uintptr_t>(rsrc) & ~uintptr_t(15));
@@ -521,6 +531,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
         if (j == 0 && row < p.batch) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(half ? mbar_hi : mbar, M * 4);
+            if constexpr (C::PLANAR)      // split-complex rows: the two "halves" are the plane of real parts and the plane of imaginary parts
+                bulk_load(half ? xb : inb, half ? p.in_im + row * p.in_stride : reinterpret_cast<const float*>(p.in) + row * p.in_stride,
+                          M * 4, half ? mbar_hi : mbar, l2pol);
+            else
             bulk_load(half ? xb : inb, p.in + row * p.in_stride + half * (M / 2), M * 4, half ? mbar_hi : mbar, l2pol);
         }
     };
@@ -589,14 +603,29 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             phase ^= 1u;
             static_for<0, R0>([&](auto t_) {
                 constexpr int t = decltype(t_)::value;
-                v[bitrev<R0>(t)] = t < R0 / 2 ? inb[j + t * T] : xb[j + (t - R0 / 2) * T];
+                if constexpr (C::PLANAR)
+                    v[bitrev<R0>(t)] = make_float2(reinterpret_cast<const float*>(inb)[j + t * T], reinterpret_cast<const float*>(xb)[j + t * T]);
+                else
+                    v[bitrev<R0>(t)] = t < R0 / 2 ? inb[j + t * T] : xb[j + (t - R0 / 2) * T];
             });
             group_sync<T>(g);                      // both halves are in registers
             issue_half(item + (long long) gridDim.x * G, 0);
         } else if constexpr (C::PF != PF_NONE) {
             if (valid) mbar_wait(mbar, phase);
             phase ^= 1u;
-            stage_gather<M, T, E, R0, LOGPAD, SRC_INBUF>(v, src, inb, j, valid);
+            if constexpr (C::PLANAR) {
+                const float* fb = reinterpret_cast<const float*>(inb);
+                static_for<0, E / R0>([&](auto q_) {
+                    constexpr int q = decltype(q_)::value;
+                    const int jq = j + q * T;
+                    static_for<0, R0>([&](auto t_) {
+                        constexpr int t = decltype(t_)::value;
+                        v[q * R0 + bitrev<R0>(t)] = make_float2(fb[jq + t * (M / R0)], fb[M + jq + t * (M / R0)]);
+                    });
+                });
+            } else {
+                stage_gather<M, T, E, R0, LOGPAD, SRC_INBUF>(v, src, inb, j, valid);
+            }
             group_sync<T>(g);                      // every thread of the group has drained the staging buffer
             if constexpr (C::PF == PF_DOUBLE) issue_next(item);
         } else if constexpr (C::PLANAR) {

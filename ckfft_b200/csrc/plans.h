@@ -20,7 +20,7 @@
     X(2048,  32, 32, 32,  2,  4, 2, 0) \
     X(4096,  32, 32, 32,  4,  2, 2, 0) \
     X(8192,  32, 32, 32,  8,  1, 2, 0) \
-    X(16384, 32, 32, 32, 16,  1, 1, 0)
+    X(16384, 32, 32, 32, 16,  1, 1, 1)
 
 // Bulk-prefetch variants (Cfg::PF): each group's next transform is fetched by cp.async.bulk into a dense
 // staging buffer while the current one is computed.  Used for complex and real-forward transforms whose
@@ -32,7 +32,12 @@
 // its HBM traffic with arithmetic is a prefetched successor in shared memory; a whole second row does not fit next to
 // the exchange buffer, so the row is prefetched in two halves (see fft_kernel.cuh).  0.64 -> 0.70 of the copy peak.
 // (A half-width exchange buffer -- real parts, then imaginary parts -- with a full staged row measured 0.67.)
+// Stage-1 twiddles from register bases (TWR) take 31 LUT reads per thread and transform off the shared-memory port:
+// complex .70 -> .77 (it costs 96 bytes of spills at the 128-register cap); the real-forward kernel, which also carries
+// the split, measured .686 without and .672 with it and keeps the LUT.
 #define CKB_SPLIT_PREFETCH_PLANS(X) \
+    X(16384, 32, 32, 32, 16,  1, 1, 1)
+#define CKB_SPLIT_PREFETCH_PLANS_R2C(X) \
     X(16384, 32, 32, 32, 16,  1, 1, 0)
 
 // In-place prefetch variants (Cfg::PF == PF_INPLACE), complex transforms only.  Measured on B200 (fraction of
@@ -44,6 +49,14 @@
     X(2048,  32, 32, 32,  2,  4, 2, 0) \
     X(4096,  32, 32, 32,  4,  2, 2, 0) \
     X(8192,  32, 32, 32,  8,  1, 2, 1)
+// Split-complex ("planar") rows with in-place prefetch: two bulk copies per row (real parts, imaginary parts); rows must
+// be 16-byte aligned (pointers and strides in multiples of 4 floats).  Measured (plain loads -> prefetch): 2048 .85 -> .94,
+// 4096 .67 -> .89, 8192 .71 -> .87; shorter rows lose (256 .90 -> .83, 512 .91 -> .86, 1024 .90 -> .88) and keep the plain
+// loads.  16384 points use the split prefetch with the two planes as the two halves.
+#define CKB_INPLACE_PREFETCH_PLANS_PLANAR(X) \
+    X(2048,  32, 32, 32,  2,  4, 2, 0) \
+    X(4096,  32, 32, 32,  4,  2, 2, 0) \
+    X(8192,  32, 32, 32,  8,  1, 2, 1)
 // Real-forward in-place prefetch (needs the register split, i.e. an even number of last-stage butterflies).
 #define CKB_INPLACE_PREFETCH_PLANS_R2C(X) \
     X(2048,  32, 32, 32,  2,  4, 2, 0) \
@@ -51,10 +64,13 @@
     X(8192,  32, 32, 32,  8,  1, 2, 1)
 
 // Real-inverse in-place prefetch (rows are bulk-copied from the 16-byte boundary below them, twisted in place).
+// (16384: the row does not leave room for a second buffer and the split prefetch needs the halves at different times,
+// but the twist needs the mirror pairs together; in-place prefetch measured .47 -> .55; with register twiddles on top .49.)
 #define CKB_INPLACE_PREFETCH_PLANS_C2R(X) \
     X(2048,  32, 32, 32,  2,  4, 2, 0) \
     X(4096,  32, 32, 32,  4,  2, 2, 0) \
-    X(8192,  32, 32, 32,  8,  1, 2, 1)
+    X(8192,  32, 32, 32,  8,  1, 2, 1) \
+    X(16384, 32, 32, 32, 16,  1, 1, 0)
 
 #define CKB_MAX_SINGLE_PASS 16384   /* largest complex length done in one launch */
 #define CKB_MAX_TABLE 32768         /* device twiddle table W_Nt^k covers real n up to this in one pass */

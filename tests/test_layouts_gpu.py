@@ -52,16 +52,39 @@ def test_planar_vs_oracle_and_interleaved(ctx_big, orc_big, n, inverse):
         torch.cuda.synchronize()
         got = (ore.cpu().numpy() + 1j * oim.cpu().numpy()).astype(np.complex64)
         assert rel_rms(got, orc_big.complex(x, inverse)) <= tolerance(n), (n, batch)
-        # The planar kernels are the plain-load instantiations of the plan table.  An interleaved input that is only
-        # 8-byte aligned takes the same instantiation (bulk prefetch needs 16-byte rows), so the two must agree bit for bit.
+        # Below 2048 points the planar kernels are the plain-load instantiations of the plan table; an interleaved input
+        # that is only 8-byte aligned takes the same instantiation (bulk prefetch needs 16-byte rows).  From 2048 points
+        # on, 16-byte aligned planes are bulk-prefetched like 16-byte aligned interleaved rows (same plan, same
+        # arithmetic).  Either way the two layouts must agree bit for bit.
         f = ctx_big.complex_inverse if inverse else ctx_big.complex_forward
-        pad = torch.empty(batch * n + 1, dtype=torch.complex64, device="cuda")
-        xi = pad[1:].view(batch, n)
+        off = 1 if n < 2048 else 2
+        pad = torch.empty(batch * n + 2, dtype=torch.complex64, device="cuda")
+        xi = pad[off:off + batch * n].view(batch, n)
         xi.copy_(torch.from_numpy(x))
-        assert xi.data_ptr() % 16 == 8
+        assert xi.data_ptr() % 16 == (8 if n < 2048 else 0) and re.data_ptr() % 16 == 0 and im.data_ptr() % 16 == 0
         inter = f(xi).cpu().numpy()
         assert np.array_equal(got.view(np.uint32), inter.view(np.uint32)), "planar and interleaved kernels differ"
         assert np.array_equal(re.cpu().numpy(), x.real) and np.array_equal(im.cpu().numpy(), x.imag), "input modified"
+
+
+@pytest.mark.parametrize("n", [2048, 4096, 8192, 16384])
+def test_planar_unaligned_rows_take_the_plain_kernels(ctx_big, orc_big, n):
+    # planes whose rows are not 16-byte aligned (odd pitch / offset pointer) cannot be bulk-copied: plain-load kernels
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+    batch, pitch = 3, n + 1
+    x = uniform_complex(rng, (batch, n))
+    re = torch.zeros(batch * pitch + 1, dtype=torch.float32, device="cuda")[1:].view(batch, pitch)
+    im = torch.zeros(batch * pitch + 1, dtype=torch.float32, device="cuda")[1:].view(batch, pitch)
+    re[:, :n] = torch.from_numpy(np.ascontiguousarray(x.real)).cuda()
+    im[:, :n] = torch.from_numpy(np.ascontiguousarray(x.imag)).cuda()
+    ore = torch.empty((batch, n), dtype=torch.float32, device="cuda")
+    oim = torch.empty((batch, n), dtype=torch.float32, device="cuda")
+    assert lib.CkFftB200ComplexForwardPlanarBatchAsync(ctx_big.handle, n, re.data_ptr(), im.data_ptr(), ore.data_ptr(), oim.data_ptr(),
+                                                       batch, pitch, n, None) == 1, ck.last_error()
+    torch.cuda.synchronize()
+    got = (ore.cpu().numpy() + 1j * oim.cpu().numpy()).astype(np.complex64)
+    assert rel_rms(got, orc_big.complex(x, False)) <= tolerance(n)
 
 
 def test_planar_in_place_strided_and_errors(ctx_big, orc_big):
