@@ -328,19 +328,27 @@ __device__ __forceinline__ void put_bin(cf* __restrict__ dst, int k, cf y)
 // Z[p + u*STR] in block 2s and Z[pbar + u*STR] in block 2s+1 (natural u order).  Writes Y[0 .. M].
 //   Y[k] = (Z[k] + conj Z[M-k]) - i W_2M^k (Z[k] - conj Z[M-k]);  with c = i W^k * diff:
 //   Y[k] = sum - c,  Y[M-k] = conj(sum + c)          (the two statements of fft_real_default.cpp:30-58)
-template <int M, int T, int E, int R, bool AUDIO>
-__device__ __forceinline__ void r2c_paired_epilogue(const cf (&v)[E], cf* __restrict__ dst, const cf* __restrict__ table,
-                                                    int sh_real, int j, bool valid)
+// Split factor W_2M^k of bin k = j + s*T + u*STR: a table value (CONST_TW = false), or the thread's own W_2M^j (`wj`, an
+// exact table value loaded once per kernel) times the compile-time constant W_64^(s*32/E + u*32/R) -- no table traffic
+// per transform, one extra rounding like the register stage twiddles.  Which one is faster depends on the registers the
+// plan has left (Cfg::RTWC, by measurement).
+template <int M, int T, int E, int R, bool AUDIO, bool CONST_TW>
+__device__ __forceinline__ void r2c_paired_epilogue(const cf (&v)[E], cf* __restrict__ dst, const cf* __restrict__ table, int sh_real,
+                                                    cf wj, int j, bool valid)
 {
     constexpr int B = E / R, STR = M / R;
     static_assert(B % 2 == 0, "butterflies come in mirror pairs");
-    auto emit = [&](cf z0, cf z1, int k) {
-        const cf w = __ldg(table + (k << sh_real));        // W_2M^k; f = i w = (-w.y, w.x)
+    static_assert(!CONST_TW || (32 % E == 0 && 16 % R == 0), "split factors are multiples of 1/64 turn");
+    auto emit = [&](cf z0, cf z1, int k, cf w) {                // w = W_2M^k; f = i w = (-w.y, w.x)
         const cf sum = make_float2(z0.x + z1.x, z0.y - z1.y);
         const cf dif = make_float2(z0.x - z1.x, z0.y + z1.y);
         const cf c = cmul(make_float2(-w.y, w.x), dif);
         put_bin<AUDIO>(dst, k, make_float2(sum.x - c.x, sum.y - c.y));
         put_bin<AUDIO>(dst, M - k, make_float2(sum.x + c.x, -(sum.y + c.y)));
+    };
+    auto factor = [&](auto k64_, int k) -> cf {
+        if constexpr (CONST_TW) return cmul_w64<decltype(k64_)::value>(wj);
+        else                    return __ldg(table + (k << sh_real));
     };
     if (!valid) return;
     static_for<0, B / 2>([&](auto s_) {
@@ -355,11 +363,20 @@ __device__ __forceinline__ void r2c_paired_epilogue(const cf (&v)[E], cf* __rest
             static_for<0, R>([&](auto u_) {
                 constexpr int u = decltype(u_)::value;
                 if constexpr (u < R / 2) {
-                    emit(v[A + u], pick(v[Bk + R - 1 - u], v[A + (R - u) % R]), p + u * STR);     // self: Y[u*STR] (u = 0: Y[0], Y[M])
+                    emit(v[A + u], pick(v[Bk + R - 1 - u], v[A + (R - u) % R]), p + u * STR,
+                         factor(Int<u * (32 / R)>{}, p + u * STR));                                // self: Y[u*STR] (u = 0: Y[0], Y[M])
                 } else {
                     constexpr int w = u - R / 2;
-                    emit(pick(v[A + u], v[Bk + w]), pick(v[Bk + R - 1 - u], v[Bk + R - 1 - w]),
-                         self ? STR / 2 + w * STR : p + u * STR);
+                    const int k = self ? STR / 2 + w * STR : p + u * STR;
+                    cf f;
+                    if constexpr (CONST_TW) {
+                        // self: bin STR/2 + w*STR, factor W_64^(16/R + w*32/R) (wj = 1 there: the product is the constant itself)
+                        constexpr int ks = 16 / R + w * (32 / R), kn = u * (32 / R);
+                        f = cmul(wj, self ? make_float2(cos64(ks), -sin64(ks)) : make_float2(cos64(kn), -sin64(kn)));
+                    } else {
+                        f = __ldg(table + (k << sh_real));
+                    }
+                    emit(pick(v[A + u], v[Bk + w]), pick(v[Bk + R - 1 - u], v[Bk + R - 1 - w]), k, f);
                 }
             });
             if (self) {
@@ -369,7 +386,7 @@ __device__ __forceinline__ void r2c_paired_epilogue(const cf (&v)[E], cf* __rest
         } else {
             static_for<0, R>([&](auto u_) {
                 constexpr int u = decltype(u_)::value;
-                emit(v[A + u], v[Bk + R - 1 - u], p + u * STR);
+                emit(v[A + u], v[Bk + R - 1 - u], p + u * STR, factor(Int<s * (32 / E) + u * (32 / R)>{}, p + u * STR));
             });
         }
     });
@@ -425,6 +442,11 @@ struct Cfg {
     // real forward: split in registers on mirror-paired butterflies when the last stage gives a thread >= 2 of them
     // (measured exception: M = 512 runs faster with the shared-memory split, .93 vs .78 of the copy peak)
     static constexpr bool PAIRED = MODE_ == MODE_R2C && ((E_ / RLAST) % 2 == 0) && M_ != 512;
+    // real split / twist factors W_2M^k: from the table, or the thread's own W_2M^j times compile-time constants (see
+    // r2c_paired_epilogue).  By measurement (real n = 2M): forward 128 .75 -> .79, 256 .85 -> .89, 16384 .72 -> .73;
+    // inverse 64 .57 -> .59, 128 .73 -> .78, 256 .73 -> .75, 8192 .79 -> .80, 16384 .71 -> .72; slower elsewhere (spills).
+    static constexpr bool RTWC = MODE_ == MODE_R2C ? (M_ == 64 || M_ == 128 || M_ == 8192)
+                               : MODE_ == MODE_C2R ? (M_ == 32 || M_ == 64 || M_ == 128 || M_ == 4096 || M_ == 8192) : false;
     static constexpr int LOGPAD = ilog2(R0);
     static constexpr int XBUF = M + (M >> LOGPAD) + 2;          // complex slots per group (+ slot M for the real modes)
     static constexpr int LUT1 = TWR_ ? 0 : (R1 - 1) * R0;       // stage 1: Ns = R0
@@ -487,6 +509,16 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
 
     const int sh_last = p.log2_nt - ilog2(M);        // W_M^k   = table[k << sh_last]
     const int sh_real = p.log2_nt - ilog2(2 * M);    // W_2M^k  = table[k << sh_real]  (real modes)
+
+    // real modes: the thread's own split / twist factor W_2M^j; bin j + i*T takes it times W_64^(i*32/E)
+    cf wj = make_float2(1.f, 0.f);
+    if constexpr (C::RTWC) wj = __ldg(p.table + (j << sh_real));
+    static_assert(!C::RTWC || 32 % E == 0, "split / twist factors are multiples of 1/64 turn");
+    auto real_factor = [&](auto i_, int k) -> cf {                 // forward W_2M^k, k = j + i*T
+        if constexpr (C::RTWC) return cmul_w64<decltype(i_)::value * (32 / E)>(wj);
+        else                   return __ldg(p.table + (k << sh_real));
+    };
+    (void) real_factor;
 
     cf twb[TwSplit<R1>::NB];
     if constexpr (C::TWR) load_tw_bases<R1, INV>(twb, p.table, j & (R0 - 1), p.log2_nt - ilog2(R0 * R1));
@@ -562,7 +594,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             static_for<0, E / 2>([&](auto i_) {
                 const int k = j + decltype(i_)::value * T;       // 0 .. M/2-1
                 const cf y0 = yb[k], y1 = yb[M - k];
-                const cf w = __ldg(p.table + (k << sh_real));
+                const cf w = real_factor(i_, k);                 // forward W_2M^k
                 const cf sum = make_float2(y0.x + y1.x, y0.y - y1.y);
                 const cf dif = make_float2(y0.x - y1.x, y0.y + y1.y);
                 const cf c = cmul(make_float2(w.y, w.x), dif);
@@ -583,7 +615,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
                 const int k = j + decltype(i_)::value * T;       // 0 .. M/2-1
                 cf y0 = make_float2(0.f, 0.f), y1 = y0;
                 if (valid) { y0 = ld_stream(src + k); y1 = ld_stream(src + (M - k)); }
-                const cf w = __ldg(p.table + (k << sh_real));    // forward W_2M^k; e = conj(w); f = i e = (w.y, w.x)
+                const cf w = real_factor(i_, k);                 // forward W_2M^k; e = conj(w); f = i e = (w.y, w.x)
                 const cf sum = make_float2(y0.x + y1.x, y0.y - y1.y);
                 const cf dif = make_float2(y0.x - y1.x, y0.y + y1.y);
                 const cf c = cmul(make_float2(w.y, w.x), dif);
@@ -656,7 +688,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
         else                  stage_math<T, E, R1, R0, INV, TW_LUT, PAIR1>(v, lut1, p.table, 0, j);
         if constexpr (C::NSTAGE == 2) {
             if constexpr (PAIR1) {
-                r2c_paired_epilogue<M, T, E, R1, C::AUDIO>(v, dst, p.table, sh_real, j, valid);
+                r2c_paired_epilogue<M, T, E, R1, C::AUDIO, C::RTWC>(v, dst, p.table, sh_real, wj, j, valid);
             } else if constexpr (MODE == MODE_R2C) {
                 group_sync<T>(g);
                 stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XNAT>(v, dst, xb, j, valid);
@@ -676,7 +708,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             if constexpr (C::POW2) stage_math_pow<E, R2, INV>(v, pw);
             else                   stage_math<T, E, R2, R0 * R1, INV, TW_LUT, C::PAIRED>(v, lut2, p.table, sh_last, j);
             if constexpr (C::PAIRED) {
-                r2c_paired_epilogue<M, T, E, R2, C::AUDIO>(v, dst, p.table, sh_real, j, valid);
+                r2c_paired_epilogue<M, T, E, R2, C::AUDIO, C::RTWC>(v, dst, p.table, sh_real, wj, j, valid);
             } else if constexpr (MODE == MODE_R2C) {
                 group_sync<T>(g);
                 stage_scatter<M, T, E, R2, R0 * R1, LOGPAD, DST_XNAT>(v, dst, xb, j, valid);
@@ -695,7 +727,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
                 const int k = j + decltype(i_)::value * T;       // 0 .. M/2-1
                 const cf z0 = xb[padidx<LOGPAD>(k)];
                 const cf z1 = xb[padidx<LOGPAD>((M - k) & (M - 1))];
-                const cf w = __ldg(p.table + (k << sh_real));    // e = W_2M^k; f = i e = (-w.y, w.x)
+                const cf w = real_factor(i_, k);                 // e = W_2M^k; f = i e = (-w.y, w.x)
                 const cf sum = make_float2(z0.x + z1.x, z0.y - z1.y);
                 const cf dif = make_float2(z0.x - z1.x, z0.y + z1.y);
                 const cf c = cmul(make_float2(-w.y, w.x), dif);

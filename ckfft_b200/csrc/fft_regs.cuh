@@ -47,9 +47,31 @@ __host__ __device__ constexpr float cos32(int k)
 }
 __host__ __device__ constexpr float sin32(int k) { return cos32(k - 8); }
 
+// cos / sin(2*pi*k/64), k any integer (the real split / twist factors a thread needs are its own W_2M^j times these)
+__host__ __device__ constexpr float cos64(int k)
+{
+    constexpr float t[17] = { 1.0f, 0.99518472667219692873f, 0.98078528040323043058f, 0.95694033573220882438f, 0.92387953251128673848f, 0.88192126434835504956f, 0.83146961230254523567f, 0.77301045336273699338f, 0.70710678118654757274f, 0.63439328416364548779f, 0.55557023301960228867f, 0.47139673682599780857f, 0.38268343236508983729f, 0.29028467725446233105f, 0.19509032201612833135f, 0.09801714032956077016f, 0.0f };
+    k &= 63;
+    if (k > 32) k = 64 - k;
+    return k > 16 ? -t[32 - k] : t[k];
+}
+__host__ __device__ constexpr float sin64(int k) { return cos64(k - 16); }
+
 __device__ __forceinline__ cf cmul(cf a, cf w)
 {
     return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+}
+
+// a * W_64^K (forward sign, exp(-2 pi i K/64)), K a compile-time constant: trivial factors cost nothing
+template <int K>
+__device__ __forceinline__ cf cmul_w64(cf a)
+{
+    constexpr int k = K & 63;
+    if constexpr (k == 0) return a;
+    else if constexpr (k == 16) return make_float2(a.y, -a.x);      // * -i
+    else if constexpr (k == 32) return make_float2(-a.x, -a.y);
+    else if constexpr (k == 48) return make_float2(-a.y, a.x);      // * +i
+    else return cmul(a, make_float2(cos64(k), -sin64(k)));
 }
 
 // (a, b) <- (a + w b, a - w b) with w = exp(-+ 2 pi i K/32), K in [0, 16), sign by INV

@@ -42,7 +42,8 @@
 
 // In-place prefetch variants (Cfg::PF == PF_INPLACE), complex transforms only.  Measured on B200 (fraction of
 // the 6.55 TB/s copy peak, without -> with): 256 .89->.94, 512 .87->.95, 2048 .90->.95, 4096 .66->.95,
-// 8192 .74->.87; rows shorter than 2 KiB lose (too many tiny bulk copies), 16384 loses (.64->.59).
+// 8192 .74->.87; rows shorter than 2 KiB lose (too many tiny bulk copies), 16384 loses (.64->.59).  Register stage
+// twiddles (TWR) for 2048 / 4096 complex: .958 -> .922, .947 -> .944, so those keep the LUT.
 #define CKB_INPLACE_PREFETCH_PLANS(X) \
     X(256,   16, 16, 16,  1,  8, 4, 1) \
     X(512,   32, 32, 16,  1,  8, 4, 0) \
@@ -58,17 +59,18 @@
     X(4096,  32, 32, 32,  4,  2, 2, 0) \
     X(8192,  32, 32, 32,  8,  1, 2, 1)
 // Real-forward in-place prefetch (needs the register split, i.e. an even number of last-stage butterflies).
+// (register stage twiddles, TWR: 2048 .87 -> .89, 4096 .77 -> .80; real inverse .83 -> .85, .76 -> .79)
 #define CKB_INPLACE_PREFETCH_PLANS_R2C(X) \
-    X(2048,  32, 32, 32,  2,  4, 2, 0) \
-    X(4096,  32, 32, 32,  4,  2, 2, 0) \
+    X(2048,  32, 32, 32,  2,  4, 2, 1) \
+    X(4096,  32, 32, 32,  4,  2, 2, 1) \
     X(8192,  32, 32, 32,  8,  1, 2, 1)
 
 // Real-inverse in-place prefetch (rows are bulk-copied from the 16-byte boundary below them, twisted in place).
 // (16384: the row does not leave room for a second buffer and the split prefetch needs the halves at different times,
 // but the twist needs the mirror pairs together; in-place prefetch measured .47 -> .55; with register twiddles on top .49.)
 #define CKB_INPLACE_PREFETCH_PLANS_C2R(X) \
-    X(2048,  32, 32, 32,  2,  4, 2, 0) \
-    X(4096,  32, 32, 32,  4,  2, 2, 0) \
+    X(2048,  32, 32, 32,  2,  4, 2, 1) \
+    X(4096,  32, 32, 32,  4,  2, 2, 1) \
     X(8192,  32, 32, 32,  8,  1, 2, 1) \
     X(16384, 32, 32, 32, 16,  1, 1, 0)
 
