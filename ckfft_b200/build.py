@@ -35,6 +35,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-fvisibi
 UNITS = [
     ("api.o", "api.cu", []),
     ("tiny.o", "tiny.cu", []),
+    ("small.o", "small.cu", []),
     ("four_step.o", "four_step.cu", []),
     ("dist_glue.o", "dist_glue.cu", []),
     ("dist_fused.o", "dist_fused.cu", []),

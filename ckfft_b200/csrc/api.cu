@@ -210,9 +210,19 @@ cudaError_t enqueue(const _CkFftContext* c, Kind kind, int n, const void* in, vo
     if (kind == K_C2C_FWD || kind == K_C2C_INV) {
         KernelParams p{ (const cf*) in, (cf*) out, table, c->log2Table, batch, in_stride, out_stride };
         const bool inv = kind == K_C2C_INV;
+        if (n >= 8 && n <= 32 && small_enabled()) return launch_small_c2c(n, inv, p, s);
         if (n <= 8) return launch_tiny_c2c(n, inv, p, s);
         if (n <= CKB_MAX_SINGLE_PASS) return inv ? launch_c2c_inv(n, p, s) : launch_c2c_fwd(n, p, s);
         return enqueue_large_c2c(c, inv, n, (const cf*) in, (cf*) out, batch, in_stride, out_stride, s);
+    }
+    if (n >= 16 && n <= 64 && small_enabled() && ((kind == K_R2C ? in_stride : out_stride) & 1) == 0) {
+        // rows of the real array on 8-byte boundaries: both arrays addressed in 8-byte units
+        if (kind == K_R2C) {
+            KernelParams p{ (const cf*) in, (cf*) out, table, c->log2Table, batch, in_stride / 2, out_stride };
+            return launch_small_r2c(n / 2, p, s);
+        }
+        KernelParams p{ (const cf*) in, (cf*) out, table, c->log2Table, batch, in_stride, out_stride / 2 };
+        return launch_small_c2r(n / 2, p, s);
     }
     if (n <= 16) {
         return kind == K_R2C
@@ -706,7 +716,7 @@ int CkFftB200GetPlan(int n, int isReal, CkFftB200Plan* plan)
     plan->isReal = isReal ? 1 : 0;
     const int m = isReal ? (n >= 2 ? n / 2 : 1) : n;
     plan->complexPoints = m;
-    const bool tiny = isReal ? n <= 16 : n <= 8;
+    const bool tiny = isReal ? n <= 64 : n <= 32;      // one thread per transform (tiny_kernel.cuh, small_kernel.cuh)
     if (tiny) {
         plan->passes = 1;
         plan->radix[0][0] = m;
@@ -788,7 +798,8 @@ static int run_planar(CkFftContext* c, bool inverse, int n, const float* inRe, c
     ckb::KernelParams p{ (const ckb::cf*) inRe, (ckb::cf*) outRe, c->dTable, c->log2Table, (long long) batch,
                          (long long) inStride, (long long) outStride, nullptr, inIm, outIm };
     cudaError_t e;
-    if (n <= 8) e = ckb::launch_tiny_c2c(n, inverse, p, (cudaStream_t) stream);
+    if (n >= 8 && n <= 32 && ckb::small_enabled()) e = ckb::launch_small_c2c(n, inverse, p, (cudaStream_t) stream);
+    else if (n <= 8) e = ckb::launch_tiny_c2c(n, inverse, p, (cudaStream_t) stream);
     else        e = inverse ? ckb::launch_c2c_inv_planar(n, p, (cudaStream_t) stream) : ckb::launch_c2c_fwd_planar(n, p, (cudaStream_t) stream);
     if (e != cudaSuccess) { set_error("kernel launch", e); return 0; }
     return 1;

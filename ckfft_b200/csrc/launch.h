@@ -24,6 +24,12 @@ cudaError_t launch_tiny_r2c(int n, const float* in, cf* out, const cf* table, in
 cudaError_t launch_tiny_c2r(int n, const cf* in, float* out, const cf* table, int log2_nt, long long batch,
                             long long in_stride, long long out_stride, cudaStream_t s);
 
+// short lengths, one thread per transform over shared-memory tiles (small.cu): complex 8 .. 32, real 16 .. 64 points
+bool small_enabled();
+cudaError_t launch_small_c2c(int M, bool inverse, const KernelParams& p, cudaStream_t s);
+cudaError_t launch_small_r2c(int M, const KernelParams& p, cudaStream_t s);      // strides in 8-byte units
+cudaError_t launch_small_c2r(int M, const KernelParams& p, cudaStream_t s);
+
 void count_launch();                  // api.cu: global launch counter
 int sm_count_of_current_device();     // api.cu: cached multiProcessorCount
 
