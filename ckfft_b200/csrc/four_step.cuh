@@ -85,12 +85,18 @@ struct TileCfg {
     static constexpr int LOGPAD = ilog2(R0);
     static_assert(R1 % 4 == 0, "the inter-pass twiddle factorisation works on groups of four bins");
     static constexpr int XRAW = L + (L >> LOGPAD) + 1;
-    static constexpr int XBUF = XRAW | 1;                  // odd: the C columns of a row chunk hit distinct banks
+    // Column pitch of the exchange buffer.  With the along-the-columns thread map a half-warp (one 128-byte wavefront of
+    // 8-byte accesses) holds 16 adjacent columns of one row (C >= 16), or 8 columns of two adjacent rows (C = 8), and a row
+    // step moves the address by 1 (mod 16, in 8-byte words): an odd pitch spreads 16 columns over the 16 bank pairs; for
+    // C = 8 the pitch must be 2 (mod 4) so that the two rows interleave (an odd pitch there is a 2-way conflict on almost
+    // every access: ncu counted 35 % of the shared-memory wavefronts of the 1024 x 1024 kernel as conflicts).
+    static constexpr int XBUF = C_ >= 16 ? (XRAW | 1) : XRAW + ((6 - XRAW % 4) % 4);
     static constexpr int LUT1 = (R1 - 1) * R0;
     static constexpr int SMEM_BYTES = 8 * (LUT1 + C * XBUF) + (PFT_ ? 16 : 0);
     static constexpr int BOX_ROWS = L < 256 ? L : 256;         // TMA boxes are at most 256 elements per dimension
     static_assert((LUT1 * 8) % 128 == 0, "the tile buffer must start on a 128-byte boundary for the tensor copies");
     static_assert(R0 * R1 == L && T <= 32 && THREADS <= 1024, "tile plan");
+    static_assert(C_ >= 16 ? XBUF % 2 == 1 : (C_ == 8 && XBUF % 4 == 2), "bank-conflict-free column pitch");
     static_assert((L * C) % THREADS == 0 && (L * C) / THREADS == E, "one tile = E elements per thread");
 };
 
