@@ -68,6 +68,7 @@
 // Real-inverse in-place prefetch (rows are bulk-copied from the 16-byte boundary below them, twisted in place).
 // (16384: the row does not leave room for a second buffer and the split prefetch needs the halves at different times,
 // but the twist needs the mirror pairs together; in-place prefetch measured .47 -> .55; with register twiddles on top .49.)
+// (shorter rows lose: in-place prefetch at M = 128 / 256 / 512 / 1024 measured .75 -> .63, .95 -> .69, .85 -> .70, .95 -> .81)
 #define CKB_INPLACE_PREFETCH_PLANS_C2R(X) \
     X(2048,  32, 32, 32,  2,  4, 2, 1) \
     X(4096,  32, 32, 32,  4,  2, 2, 1) \

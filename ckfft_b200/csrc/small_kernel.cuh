@@ -25,7 +25,9 @@ struct SmallCfg {
     static constexpr int OUT_E = MODE == MODE_R2C ? M + 1 : M;         // 8-byte elements per output row
     static constexpr int PITCH = (M + 1) | 1;                          // row pitch in the tile: odd, >= M + 1
     static constexpr int SMEM_BYTES = ROWS * PITCH * 8;
-    static constexpr int MINB = (M == 32 && MODE != MODE_C2C) ? 3 : 4;     // 32 points + split / twist: 168 registers, no spills
+    // 32 points + split / twist want ~170 registers: two CTAs per SM without spills (.87 / .85 of the copy peak for real
+    // n = 64) beat three with 32-40 bytes of spills (.79 / .77) and four with ~200 (slower still)
+    static constexpr int MINB = (M == 32 && MODE != MODE_C2C) ? 2 : 4;
     static_assert(M >= 4 && M <= 32 && (M & (M - 1)) == 0, "one register network per transform");
 };
 

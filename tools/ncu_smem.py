@@ -5,12 +5,12 @@ import csv, io, os, subprocess, sys
 path = sys.argv[1]; skip = sys.argv[2] if len(sys.argv) > 2 else "0"; top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
 raw = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass,cuda", "--launch-skip", skip, "--launch-count", "1"],
                      capture_output=True, text=True).stdout
-cur, hdr, out = "?", None, []
+cur, hdr, out, named = "?", None, [], False
 for r in csv.reader(io.StringIO(raw)):
     if not r: continue
     if r[0] == "File Path": cur = os.path.basename(r[1]); continue
     if r[0] == "Function Name":
-        if hdr is None and cur != "seen": print(r[1][:160]); cur = "seen"
+        if not named: print(r[1][:160]); named = True
         continue
     if r[0] == "Line No": hdr = r; continue
     if hdr and len(r) == len(hdr) and r[2] == "-":
