@@ -210,7 +210,7 @@ cudaError_t enqueue(const _CkFftContext* c, Kind kind, int n, const void* in, vo
     if (kind == K_C2C_FWD || kind == K_C2C_INV) {
         KernelParams p{ (const cf*) in, (cf*) out, table, c->log2Table, batch, in_stride, out_stride };
         const bool inv = kind == K_C2C_INV;
-        if (n >= 8 && n <= 32 && small_enabled()) return launch_small_c2c(n, inv, p, s);
+        if (n >= 8 && n <= 64 && small_enabled()) return launch_small_c2c(n, inv, p, s);
         if (n <= 8) return launch_tiny_c2c(n, inv, p, s);
         if (n <= CKB_MAX_SINGLE_PASS) return inv ? launch_c2c_inv(n, p, s) : launch_c2c_fwd(n, p, s);
         return enqueue_large_c2c(c, inv, n, (const cf*) in, (cf*) out, batch, in_stride, out_stride, s);
@@ -717,6 +717,14 @@ int CkFftB200GetPlan(int n, int isReal, CkFftB200Plan* plan)
     const int m = isReal ? (n >= 2 ? n / 2 : 1) : n;
     plan->complexPoints = m;
     const bool tiny = isReal ? n <= 64 : n <= 32;      // one thread per transform (tiny_kernel.cuh, small_kernel.cuh)
+    if (!isReal && n == 64) {                           // two threads per row: radix 32 x 2 (small_kernel.cuh)
+        plan->passes = 1;
+        plan->radix[0][0] = 32; plan->radix[0][1] = 2;
+        plan->threadsPerTransform = 2;
+        plan->elemsPerThread = 32;
+        plan->transformsPerCta = 64;
+        return 1;
+    }
     if (tiny) {
         plan->passes = 1;
         plan->radix[0][0] = m;
@@ -798,7 +806,7 @@ static int run_planar(CkFftContext* c, bool inverse, int n, const float* inRe, c
     ckb::KernelParams p{ (const ckb::cf*) inRe, (ckb::cf*) outRe, c->dTable, c->log2Table, (long long) batch,
                          (long long) inStride, (long long) outStride, nullptr, inIm, outIm };
     cudaError_t e;
-    if (n >= 8 && n <= 32 && ckb::small_enabled()) e = ckb::launch_small_c2c(n, inverse, p, (cudaStream_t) stream);
+    if (n >= 8 && n <= 64 && ckb::small_enabled()) e = ckb::launch_small_c2c(n, inverse, p, (cudaStream_t) stream);
     else if (n <= 8) e = ckb::launch_tiny_c2c(n, inverse, p, (cudaStream_t) stream);
     else        e = inverse ? ckb::launch_c2c_inv_planar(n, p, (cudaStream_t) stream) : ckb::launch_c2c_fwd_planar(n, p, (cudaStream_t) stream);
     if (e != cudaSuccess) { set_error("kernel launch", e); return 0; }

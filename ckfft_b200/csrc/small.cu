@@ -1,4 +1,4 @@
-// small.cu -- launchers of the thread-per-transform tile kernels (small_kernel.cuh): complex 8 .. 32 points,
+// small.cu -- launchers of the thread-per-transform tile kernels (small_kernel.cuh): complex 8 .. 64 points,
 // real 16 .. 64 points.
 #include "launch.h"
 #include "small_kernel.cuh"
@@ -26,14 +26,14 @@ static cudaError_t small_launch(const KernelParams& p, cudaStream_t s)
     if (grid_cap[dev] == 0) {
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SC::SMEM_BYTES)) != cudaSuccess) return e;
         int occ = 0;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SC::ROWS, SC::SMEM_BYTES)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SC::THREADS, SC::SMEM_BYTES)) != cudaSuccess) return e;
         if (occ < 1) return cudaErrorLaunchOutOfResources;
         grid_cap[dev] = occ * sm_count_of_current_device();
     }
     const long long tiles = (p.batch + SC::ROWS - 1) / SC::ROWS;
     const int grid = (int) (tiles < grid_cap[dev] ? tiles : grid_cap[dev]);
     if (grid <= 0) return cudaSuccess;
-    kern<<<grid, SC::ROWS, SC::SMEM_BYTES, s>>>(p);
+    kern<<<grid, SC::THREADS, SC::SMEM_BYTES, s>>>(p);
     count_launch();
     return cudaGetLastError();
 }
@@ -45,11 +45,14 @@ static cudaError_t small_dispatch(int M, const KernelParams& p, cudaStream_t s)
         case 8:  return small_launch<8, MODE, INV, PLANAR>(p, s);
         case 16: return small_launch<16, MODE, INV, PLANAR>(p, s);
         case 32: return small_launch<32, MODE, INV, PLANAR>(p, s);
+        case 64:
+            if constexpr (MODE == MODE_C2C) return small_launch<64, MODE, INV, PLANAR>(p, s);
+            else return cudaErrorInvalidValue;
         default: return cudaErrorInvalidValue;
     }
 }
 
-// complex M = 8, 16, 32; p.in_im != nullptr: split-complex rows (strides in floats)
+// complex M = 8, 16, 32, 64; p.in_im != nullptr: split-complex rows (strides in floats)
 cudaError_t launch_small_c2c(int M, bool inverse, const KernelParams& p, cudaStream_t s)
 {
     if (p.in_im != nullptr)

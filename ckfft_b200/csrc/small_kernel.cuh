@@ -12,6 +12,9 @@
 //     exchange), applies the real split / twist with compile-time factors W_2M^k = W_64^(k*32/M), and writes the
 //     result back over its row,
 //   * and the tile leaves shared -> global the way it came.
+// 64-point complex rows take TWO threads per row (SmallCfg::TPR = 2): each runs a 32-point network on the even / odd
+// samples, the odd half is multiplied by W_64^k (constants) and the final radix-2 step exchanges 16 values per thread
+// with one warp shuffle each -- still no table and no shared-memory exchange.
 // Same mathematics as the reference's small cases (src/ckfft/fft_default.cpp:22-167 leaves, fft_real_default.cpp:13-114).
 #pragma once
 #include "fft_kernel.cuh"
@@ -20,41 +23,52 @@ namespace ckb {
 
 template <int M, int MODE>
 struct SmallCfg {
-    static constexpr int ROWS = 128;                                   // rows per tile = threads per CTA
+    static constexpr int THREADS = 128;
+    static constexpr int TPR = M > 32 ? M / 32 : 1;                    // threads per row
+    static constexpr int ROWS = THREADS / TPR;                         // rows per tile
+    static constexpr int NV = M / TPR;                                 // complex values per thread
     static constexpr int IN_E = MODE == MODE_C2R ? M + 1 : M;          // 8-byte elements per input row
     static constexpr int OUT_E = MODE == MODE_R2C ? M + 1 : M;         // 8-byte elements per output row
-    static constexpr int PITCH = (M + 1) | 1;                          // row pitch in the tile: odd, >= M + 1
+    // row pitch in the tile (8-byte words).  One thread per row: odd, so that 16 rows spread over the 16 bank pairs.
+    // Two threads per row (adjacent lanes read adjacent words of the same row): 2 mod 16, so that 8 rows x 2 words do.
+    static constexpr int PITCH = TPR == 1 ? ((M + 1) | 1) : M + 2;
     static constexpr int SMEM_BYTES = ROWS * PITCH * 8;
     // 32 points + split / twist want ~170 registers: two CTAs per SM without spills (.87 / .85 of the copy peak for real
     // n = 64) beat three with 32-40 bytes of spills (.79 / .77) and four with ~200 (slower still)
     static constexpr int MINB = (M == 32 && MODE != MODE_C2C) ? 2 : 4;
-    static_assert(M >= 4 && M <= 32 && (M & (M - 1)) == 0, "one register network per transform");
+    static_assert(M >= 4 && M <= 64 && (M & (M - 1)) == 0, "one or two register networks per transform");
+    static_assert(TPR == 1 || (TPR == 2 && MODE == MODE_C2C && PITCH % 16 == 2), "two threads per row: complex transforms");
+    static_assert((ROWS * IN_E) % THREADS == 0 || TPR == 1, "whole copy rounds");
 };
 
 // tile <-> global, 8-byte elements, consecutive threads on consecutive elements of the [rows][E] tile
-template <int E, int PITCH, bool LOAD>
+template <int E, int PITCH, int ROWS, bool LOAD>
 __device__ __forceinline__ void small_copy(cf* tile, const cf* gin, cf* gout, long long stride, int rows, int tid)
 {
-    constexpr int ROWS = 128;
+    constexpr int THREADS = 128;
+    constexpr int PER = (ROWS * E + THREADS - 1) / THREADS;       // elements per thread (full tile)
     if (rows == ROWS) {
         if constexpr (LOAD) {
-            cf tmp[E];                        // all loads in flight before the first shared-memory store
-            static_for<0, E>([&](auto i_) {
-                const int e = decltype(i_)::value * ROWS + tid;
-                tmp[decltype(i_)::value] = __ldcs(gin + (long long) (e / E) * stride + e % E);
+            cf tmp[PER];                      // all loads in flight before the first shared-memory store
+            static_for<0, PER>([&](auto i_) {
+                const int e = decltype(i_)::value * THREADS + tid;
+                if ((decltype(i_)::value + 1) * THREADS <= ROWS * E || e < ROWS * E)
+                    tmp[decltype(i_)::value] = __ldcs(gin + (long long) (e / E) * stride + e % E);
             });
-            static_for<0, E>([&](auto i_) {
-                const int e = decltype(i_)::value * ROWS + tid;
-                tile[(e / E) * PITCH + e % E] = tmp[decltype(i_)::value];
+            static_for<0, PER>([&](auto i_) {
+                const int e = decltype(i_)::value * THREADS + tid;
+                if ((decltype(i_)::value + 1) * THREADS <= ROWS * E || e < ROWS * E)
+                    tile[(e / E) * PITCH + e % E] = tmp[decltype(i_)::value];
             });
         } else {
-            static_for<0, E>([&](auto i_) {
-                const int e = decltype(i_)::value * ROWS + tid;
-                __stcs(gout + (long long) (e / E) * stride + e % E, tile[(e / E) * PITCH + e % E]);
+            static_for<0, PER>([&](auto i_) {
+                const int e = decltype(i_)::value * THREADS + tid;
+                if ((decltype(i_)::value + 1) * THREADS <= ROWS * E || e < ROWS * E)
+                    __stcs(gout + (long long) (e / E) * stride + e % E, tile[(e / E) * PITCH + e % E]);
             });
         }
     } else {
-        for (int e = tid; e < rows * E; e += ROWS) {
+        for (int e = tid; e < rows * E; e += THREADS) {
             if constexpr (LOAD) tile[(e / E) * PITCH + e % E] = __ldcs(gin + (long long) (e / E) * stride + e % E);
             else                __stcs(gout + (long long) (e / E) * stride + e % E, tile[(e / E) * PITCH + e % E]);
         }
@@ -62,26 +76,52 @@ __device__ __forceinline__ void small_copy(cf* tile, const cf* gin, cf* gout, lo
 }
 
 // split-complex rows: the planes of real and imaginary parts are separate float arrays (strides in floats)
-template <int M, int PITCH, bool LOAD>
+template <int M, int PITCH, int ROWS, bool LOAD>
 __device__ __forceinline__ void small_copy_planar(cf* tile, const float* gre, const float* gim, float* ore, float* oim,
                                                   long long stride, int rows, int tid)
 {
-    float* ft = reinterpret_cast<float*>(tile);
-    for (int e = tid; e < rows * M; e += 128) {
-        const int r = e / M, c = e % M;
-        const long long g = (long long) r * stride + c;
+    constexpr int THREADS = 128;
+    constexpr int PER = ROWS * M / THREADS;
+    static_assert(ROWS * M % THREADS == 0, "whole copy rounds");
+    if (rows == ROWS) {
+        // 4-byte global accesses (128 contiguous bytes per plane and warp request), 8-byte shared-memory accesses
         if constexpr (LOAD) {
-            ft[2 * (r * PITCH + c)] = __ldcs(gre + g);
-            ft[2 * (r * PITCH + c) + 1] = __ldcs(gim + g);
+            cf tmp[PER];
+            static_for<0, PER>([&](auto i_) {
+                const int e = decltype(i_)::value * THREADS + tid;
+                const long long g = (long long) (e / M) * stride + e % M;
+                tmp[decltype(i_)::value] = make_float2(__ldcs(gre + g), __ldcs(gim + g));
+            });
+            static_for<0, PER>([&](auto i_) {
+                const int e = decltype(i_)::value * THREADS + tid;
+                tile[(e / M) * PITCH + e % M] = tmp[decltype(i_)::value];
+            });
         } else {
-            __stcs(ore + g, ft[2 * (r * PITCH + c)]);
-            __stcs(oim + g, ft[2 * (r * PITCH + c) + 1]);
+            static_for<0, PER>([&](auto i_) {
+                const int e = decltype(i_)::value * THREADS + tid;
+                const long long g = (long long) (e / M) * stride + e % M;
+                const cf x = tile[(e / M) * PITCH + e % M];
+                __stcs(ore + g, x.x);
+                __stcs(oim + g, x.y);
+            });
+        }
+    } else {
+        for (int e = tid; e < rows * M; e += THREADS) {
+            const int r = e / M, c = e % M;
+            const long long g = (long long) r * stride + c;
+            if constexpr (LOAD) {
+                tile[r * PITCH + c] = make_float2(__ldcs(gre + g), __ldcs(gim + g));
+            } else {
+                const cf x = tile[r * PITCH + c];
+                __stcs(ore + g, x.x);
+                __stcs(oim + g, x.y);
+            }
         }
     }
 }
 
 template <int M, int MODE, bool INV, bool PLANAR>
-__global__ void __launch_bounds__(128, SmallCfg<M, MODE>::MINB) small_kernel(const KernelParams p)
+__global__ void __launch_bounds__(SmallCfg<M, MODE>::THREADS, SmallCfg<M, MODE>::MINB) small_kernel(const KernelParams p)
 {
     using SC = SmallCfg<M, MODE>;
     constexpr int PITCH = SC::PITCH;
@@ -95,13 +135,40 @@ __global__ void __launch_bounds__(128, SmallCfg<M, MODE>::MINB) small_kernel(con
         const int rows = left < SC::ROWS ? (int) left : SC::ROWS;
 
         if constexpr (PLANAR)
-            small_copy_planar<M, PITCH, true>(tile, reinterpret_cast<const float*>(p.in) + base * p.in_stride, p.in_im + base * p.in_stride,
+            small_copy_planar<M, PITCH, SC::ROWS, true>(tile, reinterpret_cast<const float*>(p.in) + base * p.in_stride, p.in_im + base * p.in_stride,
                                               nullptr, nullptr, p.in_stride, rows, tid);
         else
-            small_copy<SC::IN_E, PITCH, true>(tile, p.in + base * p.in_stride, nullptr, p.in_stride, rows, tid);
+            small_copy<SC::IN_E, PITCH, SC::ROWS, true>(tile, p.in + base * p.in_stride, nullptr, p.in_stride, rows, tid);
         __syncthreads();
 
-        if (tid < rows) {
+        if constexpr (SC::TPR == 2) {
+            // every thread computes (rows past the end of the batch work on whatever the buffer holds and are not stored):
+            // the shuffles below then always find their partner
+            const int t = tid & 1;
+            cf* row = tile + (tid >> 1) * PITCH;
+            cf v[32];
+            static_for<0, 32>([&](auto i_) { constexpr int i = decltype(i_)::value; v[bitrev<32>(i)] = row[2 * i + t]; });
+            fft_regs<32, 0, INV>(v);                                  // A_t[k] = sum_i x[2i + t] W_32^(ik)
+            if (t) {                                                  // odd half: times W_64^k (conjugate for the inverse)
+                static_for<1, 32>([&](auto k_) {
+                    constexpr int k = decltype(k_)::value;
+                    v[k] = cmul_w64<INV ? 64 - k : k>(v[k]);
+                });
+            }
+            // X[k] = A_0[k] + B[k], X[k + 32] = A_0[k] - B[k]: thread t takes the k of its own parity, so each thread
+            // hands over the 16 values of the other parity and both write runs of adjacent words
+            static_for<0, 16>([&](auto i_) {
+                constexpr int i = decltype(i_)::value;
+                const cf send = t ? v[2 * i] : v[2 * i + 1];
+                cf recv;
+                recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+                recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+                const cf a = t ? recv : v[2 * i];
+                const cf b = t ? v[2 * i + 1] : recv;
+                row[2 * i + t] = make_float2(a.x + b.x, a.y + b.y);
+                row[2 * i + t + 32] = make_float2(a.x - b.x, a.y - b.y);
+            });
+        } else if (tid < rows) {
             cf* row = tile + tid * PITCH;
             cf v[M];
             if constexpr (MODE == MODE_C2R) {
@@ -143,10 +210,10 @@ __global__ void __launch_bounds__(128, SmallCfg<M, MODE>::MINB) small_kernel(con
         __syncthreads();
 
         if constexpr (PLANAR)
-            small_copy_planar<M, PITCH, false>(tile, nullptr, nullptr, reinterpret_cast<float*>(p.out) + base * p.out_stride,
+            small_copy_planar<M, PITCH, SC::ROWS, false>(tile, nullptr, nullptr, reinterpret_cast<float*>(p.out) + base * p.out_stride,
                                                p.out_im + base * p.out_stride, p.out_stride, rows, tid);
         else
-            small_copy<SC::OUT_E, PITCH, false>(tile, nullptr, p.out + base * p.out_stride, p.out_stride, rows, tid);
+            small_copy<SC::OUT_E, PITCH, SC::ROWS, false>(tile, nullptr, p.out + base * p.out_stride, p.out_stride, rows, tid);
         __syncthreads();                      // the next tile overwrites the buffer
     }
 }
