@@ -18,6 +18,11 @@ out = torch.empty_like(x)
 for _ in range(4):
     if kind == "c2c":
         ctx.complex_forward(x, out)
+    elif kind == "c2cp":        # split-complex arrays
+        f32 = x.view(torch.float32).view(-1)
+        o32 = out.view(torch.float32).view(-1)
+        ctx.complex_planar(f32[: batch * n].view(batch, n), f32[batch * n:].view(batch, n), False,
+                           (o32[: batch * n].view(batch, n), o32[batch * n:].view(batch, n)))
     elif kind == "c2ci":
         ctx.complex_inverse(x, out)
     elif kind == "r2c":
