@@ -171,7 +171,7 @@ def test_large_complex_in_place(log2n):
         assert rel_rms(y.cpu().numpy() / n, x.cpu().numpy()) <= tolerance(n)
 
 
-@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 32, 128, 1024, 4096, 8192, 16384, 32768])
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 32, 64, 128, 1024, 4096, 8192, 16384, 32768])
 def test_real_in_place_padded_rows(ctx_big, orc_big, n):
     """rows of n + 2 floats = n/2 + 1 complex: the forward transform overwrites the samples with the half spectrum, the
     inverse overwrites the spectrum with 2n * the samples (the reference's scaling, inc/ckfft/ckfft.h:123-125)"""
@@ -209,3 +209,64 @@ def test_in_place_argument_rules(ctx_big):
     assert lib.CkFftComplexForward(h, 1024, p, p) == 0
     assert lib.CkFftComplexForwardBatch(h, 1024, p, p, 4) == 0
     assert lib.CkFftRealForward(h, 1024, p, p) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# short rows (tile kernels, small_kernel.cuh): padded strides, ragged last tile, exactly one tile
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("batch", [1, 63, 64, 65, 127, 128, 129, 300])
+@pytest.mark.parametrize("n", [8, 16, 32, 64])
+def test_short_complex_rows_strided_and_ragged(ctx_big, orc_big, n, batch):
+    lib = _lib.load()
+    rng = np.random.default_rng(1000 * n + batch)
+    pin, pout = n + 3, n + 5                      # rows start on 8-byte boundaries only
+    x = uniform_complex(rng, (batch, n))
+    xin = torch.zeros((batch, pin), dtype=torch.complex64, device="cuda")
+    xin[:, :n] = torch.from_numpy(x).cuda()
+    out = torch.full((batch, pout), 7.0 + 0j, dtype=torch.complex64, device="cuda")
+    for inverse in (False, True):
+        fn = lib.CkFftComplexInverseBatchAsync if inverse else lib.CkFftComplexForwardBatchAsync
+        assert fn(ctx_big.handle, n, xin.data_ptr(), out.data_ptr(), batch, pin, pout, None) == 1, ck.last_error()
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        assert rel_rms(got[:, :n], orc_big.complex(x, inverse)) <= tolerance(n), (n, batch, inverse)
+        assert np.all(got[:, n:] == 7.0), "padding between rows was written"
+
+
+@pytest.mark.parametrize("batch", [1, 127, 128, 129, 300])
+@pytest.mark.parametrize("n", [16, 32, 64])
+def test_short_real_rows_strided_and_ragged(ctx_big, orc_big, n, batch):
+    lib = _lib.load()
+    rng = np.random.default_rng(2000 * n + batch)
+    bins = n // 2 + 1
+    pin, pspec, pout = n + 6, bins + 3, n + 2     # even strides of the real arrays (8-byte rows), odd spectrum pitch
+    x = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    xin = torch.zeros((batch, pin), dtype=torch.float32, device="cuda")
+    xin[:, :n] = torch.from_numpy(x).cuda()
+    spec = torch.full((batch, pspec), 7.0 + 0j, dtype=torch.complex64, device="cuda")
+    assert lib.CkFftRealForwardBatchAsync(ctx_big.handle, n, xin.data_ptr(), spec.data_ptr(), batch, pin, pspec, None) == 1, ck.last_error()
+    torch.cuda.synchronize()
+    got = spec.cpu().numpy()
+    want = orc_big.real_forward(x)
+    assert rel_rms(got[:, :bins], want) <= tolerance(n), (n, batch)
+    assert np.all(got[:, bins:] == 7.0), "padding between spectrum rows was written"
+    back = torch.full((batch, pout), 7.0, dtype=torch.float32, device="cuda")
+    assert lib.CkFftRealInverseBatchAsync(ctx_big.handle, n, spec.data_ptr(), back.data_ptr(), batch, pspec, pout, None) == 1, ck.last_error()
+    torch.cuda.synchronize()
+    b = back.cpu().numpy()
+    assert rel_rms(b[:, :n], orc_big.real_inverse(want, n)) <= tolerance(n), (n, batch)
+    assert np.all(b[:, n:] == 7.0), "padding between sample rows was written"
+
+
+def test_real_16_points_odd_strides_take_the_thread_per_transform_kernels(ctx_big, orc_big):
+    """rows of an odd number of floats are only 4-byte aligned: the 8-byte tile copies do not apply (tiny_kernel.cuh)"""
+    lib = _lib.load()
+    n, batch, pin = 16, 200, 19
+    rng = np.random.default_rng(77)
+    x = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    xin = torch.zeros((batch, pin), dtype=torch.float32, device="cuda")
+    xin[:, :n] = torch.from_numpy(x).cuda()
+    spec = torch.zeros((batch, n // 2 + 1), dtype=torch.complex64, device="cuda")
+    assert lib.CkFftRealForwardBatchAsync(ctx_big.handle, n, xin.data_ptr(), spec.data_ptr(), batch, pin, 0, None) == 1, ck.last_error()
+    torch.cuda.synchronize()
+    assert rel_rms(spec.cpu().numpy(), orc_big.real_forward(x)) <= tolerance(n)
