@@ -129,6 +129,16 @@ def test_planner_covers_every_power_of_two():
     assert p["radix"] == [[32, 32]] and p["threads_per_transform"] == 32 and p["elems_per_thread"] == 32
     q = ck.get_plan(4096, real=True)
     assert q["complex_points"] == 2048
+    # short rows (small_kernel.cuh): one register network per thread, 128 rows per CTA; 64 complex points: two threads per row
+    for n in (8, 16, 32):
+        p = ck.get_plan(n)
+        assert p["radix"][0][0] == n and p["threads_per_transform"] == 1 and p["transforms_per_cta"] == 128, p
+    p = ck.get_plan(64)
+    assert p["radix"][0][:2] == [32, 2] and p["threads_per_transform"] == 2 and p["transforms_per_cta"] == 64, p
+    q = ck.get_plan(64, real=True)
+    assert q["complex_points"] == 32 and q["threads_per_transform"] == 1
+    q = ck.get_plan(128, real=True)                      # real n = 128 stays on the cooperative kernel (8 x 8 radix split)
+    assert q["complex_points"] == 64 and q["threads_per_transform"] == 8 and q["radix"][0][:2] == [8, 8], q
 
 
 def test_no_gpu_fails_loudly():
