@@ -3,4 +3,4 @@
 The product is the C-ABI shared library `ckfft_b200/lib/libckfft_b200.so` (headers in `include/ckfft/`);
 this package is the thin Python mirror of the reference interface used by the tests and bench.
 """
-from .api import BOTH, FORWARD, INVERSE, CkFftError, Context, get_plan, kernel_launches, last_error  # noqa: F401
+from .api import BOTH, FORWARD, INVERSE, CkFftError, Context, MultiContext, get_plan, kernel_launches, last_error  # noqa: F401

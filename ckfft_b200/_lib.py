@@ -22,7 +22,10 @@ B200_SYMBOLS = ["CkFftComplexForwardBatch", "CkFftComplexInverseBatch", "CkFftRe
                 "CkFftB200DistGetLayout", "CkFftB200DistDescribe", "CkFftB200PeerAlloc", "CkFftB200PeerFree",
                 "CkFftB200PeerExport", "CkFftB200PeerOpen", "CkFftB200PeerClose", "CkFftB200DistPlanCreate",
                 "CkFftB200DistExecAsync", "CkFftB200DistPlanStatus", "CkFftB200DistPlanDestroy",
-                "CkFftB200DistPlanSetProfiling", "CkFftB200DistPlanPhases"]
+                "CkFftB200DistPlanSetProfiling", "CkFftB200DistPlanPhases",
+                "CkFftB200MultiInit", "CkFftB200MultiShutdown", "CkFftB200MultiDeviceCount", "CkFftB200MultiDevice",
+                "CkFftB200MultiContext", "CkFftB200ShardRange", "CkFftComplexForwardBatchMulti",
+                "CkFftComplexInverseBatchMulti", "CkFftRealForwardBatchMulti", "CkFftRealInverseBatchMulti"]
 
 
 class Plan(C.Structure):
@@ -108,5 +111,17 @@ def load() -> C.CDLL:
     lib.CkFftB200DistPlanPhases.argtypes = [vp, C.POINTER(C.c_float), C.c_char_p, sz]
     lib.CkFftB200DistPlanDestroy.restype = None
     lib.CkFftB200DistPlanDestroy.argtypes = [vp]
+    lib.CkFftB200MultiInit.restype = vp
+    lib.CkFftB200MultiInit.argtypes = [i, i, C.POINTER(C.c_int), i]
+    lib.CkFftB200MultiShutdown.restype = None
+    lib.CkFftB200MultiShutdown.argtypes = [vp]
+    lib.CkFftB200MultiDeviceCount.argtypes = [vp]
+    lib.CkFftB200MultiDevice.argtypes = [vp, i]
+    lib.CkFftB200MultiContext.restype = vp
+    lib.CkFftB200MultiContext.argtypes = [vp, i]
+    lib.CkFftB200ShardRange.argtypes = [sz, i, i, C.POINTER(sz), C.POINTER(sz)]
+    for name in ("CkFftComplexForwardBatchMulti", "CkFftComplexInverseBatchMulti", "CkFftRealForwardBatchMulti",
+                 "CkFftRealInverseBatchMulti"):
+        getattr(lib, name).argtypes = [vp, i, vp, vp, sz]
     _lib = lib
     return lib

@@ -116,6 +116,24 @@ class Context:
         return np.ascontiguousarray(x, dtype=np_dtype)
 
     @staticmethod
+    def _check_out(out, like, shape, np_dtype, torch_name, what="out"):
+        """A caller-supplied output goes to the C ABI as a bare pointer with dense strides: it must be exactly the
+        array the call would have allocated (dtype, shape, contiguous, same side / device as the input)."""
+        shape = tuple(int(d) for d in shape)
+        if _is_torch(like):
+            import torch
+
+            if not _is_torch(out) or not out.is_cuda or out.device != like.device:
+                raise CkFftError(f"{what} must be a CUDA tensor on {like.device}")
+            if out.dtype != getattr(torch, torch_name) or tuple(out.shape) != shape or not out.is_contiguous():
+                raise CkFftError(f"{what} must be a contiguous {torch_name} tensor of shape {shape}")
+        else:
+            if not isinstance(out, np.ndarray) or out.dtype != np.dtype(np_dtype) or tuple(out.shape) != shape \
+                    or not out.flags.c_contiguous or not out.flags.writeable:
+                raise CkFftError(f"{what} must be a writeable C-contiguous numpy {np.dtype(np_dtype).name} array of shape {shape}")
+        return out
+
+    @staticmethod
     def _empty_like(x, shape, np_dtype, torch_name):
         if _is_torch(x):
             import torch
@@ -138,6 +156,8 @@ class Context:
         batch = int(np.prod(x.shape[:-1], dtype=np.int64)) if x.ndim > 1 else 1
         if out is None:
             out = self._empty_like(x, tuple(x.shape), np.complex64, "complex64")
+        else:
+            self._check_out(out, x, tuple(x.shape), np.complex64, "complex64")
         return self._run(name, n, x, out, batch)
 
     def complex_planar(self, re, im, inverse: bool = False, out=None):
@@ -153,6 +173,11 @@ class Context:
         batch = int(np.prod(re.shape[:-1], dtype=np.int64)) if re.ndim > 1 else 1
         if out is None:
             out = (torch.empty_like(re), torch.empty_like(im))
+        else:
+            if not isinstance(out, (tuple, list)) or len(out) != 2:
+                raise CkFftError("out must be a pair (re, im)")
+            for o, name in zip(out, ("out[0]", "out[1]")):
+                self._check_out(o, re, tuple(re.shape), np.float32, "float32", name)
         fn = self._lib.CkFftB200ComplexInversePlanarBatchAsync if inverse else self._lib.CkFftB200ComplexForwardPlanarBatchAsync
         stream = torch.cuda.current_stream(re.device).cuda_stream
         if not fn(self._ctx, n, re.data_ptr(), im.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), batch, 0, 0, stream):
@@ -166,6 +191,8 @@ class Context:
         batch = int(np.prod(x.shape[:-1], dtype=np.int64)) if x.ndim > 1 else 1
         if out is None:
             out = self._empty_like(x, tuple(x.shape[:-1]) + (n // 2 + 1,), np.complex64, "complex64")
+        else:
+            self._check_out(out, x, tuple(x.shape[:-1]) + (n // 2 + 1,), np.complex64, "complex64")
         return self._run("CkFftRealForward", n, x, out, batch)
 
     def real_forward_power(self, x, window=None, out=None):
@@ -184,6 +211,8 @@ class Context:
                 raise CkFftError(f"window must have {n} samples")
         if out is None:
             out = torch.empty(tuple(x.shape[:-1]) + (n // 2 + 1,), dtype=torch.float32, device=x.device)
+        else:
+            self._check_out(out, x, tuple(x.shape[:-1]) + (n // 2 + 1,), np.float32, "float32")
         stream = torch.cuda.current_stream(x.device).cuda_stream
         ok = self._lib.CkFftB200RealForwardPowerBatchAsync(self._ctx, n, x.data_ptr(), window.data_ptr() if window is not None else None,
                                                            out.data_ptr(), batch, 0, 0, stream)
@@ -199,4 +228,77 @@ class Context:
         batch = int(np.prod(y.shape[:-1], dtype=np.int64)) if y.ndim > 1 else 1
         if out is None:
             out = self._empty_like(y, tuple(y.shape[:-1]) + (n,), np.float32, "float32")
+        else:
+            self._check_out(out, y, tuple(y.shape[:-1]) + (n,), np.float32, "float32")
         return self._run("CkFftRealInverse", n, y, out, batch)
+
+
+class MultiContext:
+    """CkFftB200Multi: the batched scheduler behind `CkFft*BatchMulti` -- one call spreads a batch of independent
+    transforms held in HOST arrays over several GPUs (contiguous shards, one context replica + one host thread per
+    device, no collective; include/ckfft/ckfft_b200.h).  `devices=None`: every visible device."""
+
+    def __init__(self, n_max: int, direction: int = BOTH, devices=None):
+        self._lib = _lib.load()
+        if devices is None:
+            arr, cnt = None, 0
+        else:
+            devices = [int(d) for d in devices]
+            arr, cnt = (C.c_int * len(devices))(*devices), len(devices)
+        self._m = self._lib.CkFftB200MultiInit(int(n_max), int(direction), arr, cnt)
+        if not self._m:
+            raise CkFftError(f"CkFftB200MultiInit({n_max}, {direction}, {devices}) returned NULL: {last_error()}")
+        self.n_max = n_max
+
+    @property
+    def devices(self) -> list[int]:
+        return [int(self._lib.CkFftB200MultiDevice(self._m, i)) for i in range(self._lib.CkFftB200MultiDeviceCount(self._m))]
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._lib.CkFftB200MultiShutdown(self._m)
+            self._m = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _run(self, name, n, x, out_shape, out_dtype, out, batch):
+        if out is None:
+            out = np.empty(out_shape, dtype=out_dtype)
+        else:
+            Context._check_out(out, x, out_shape, out_dtype, "", "out")
+        if not getattr(self._lib, name)(self._m, n, x.ctypes.data, out.ctypes.data, batch):
+            raise CkFftError(f"{name} returned 0: {last_error()}")
+        return out
+
+    @staticmethod
+    def _batch(x):
+        return int(np.prod(x.shape[:-1], dtype=np.int64)) if x.ndim > 1 else 1
+
+    def complex_forward(self, x, out=None):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        return self._run("CkFftComplexForwardBatchMulti", x.shape[-1], x, tuple(x.shape), np.complex64, out, self._batch(x))
+
+    def complex_inverse(self, x, out=None):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        return self._run("CkFftComplexInverseBatchMulti", x.shape[-1], x, tuple(x.shape), np.complex64, out, self._batch(x))
+
+    def real_forward(self, x, out=None):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n = x.shape[-1]
+        return self._run("CkFftRealForwardBatchMulti", n, x, tuple(x.shape[:-1]) + (n // 2 + 1,), np.complex64, out, self._batch(x))
+
+    def real_inverse(self, y, n: int, out=None):
+        y = np.ascontiguousarray(y, dtype=np.complex64)
+        if y.shape[-1] != n // 2 + 1:
+            raise CkFftError(f"expected {n // 2 + 1} bins for n={n}, got {y.shape[-1]}")
+        return self._run("CkFftRealInverseBatchMulti", n, y, tuple(y.shape[:-1]) + (n,), np.float32, out, self._batch(y))

@@ -34,6 +34,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-fvisibi
 # (object name, source, extra flags)
 UNITS = [
     ("api.o", "api.cu", []),
+    ("multi.o", "multi.cu", []),
     ("tiny.o", "tiny.cu", []),
     ("small.o", "small.cu", []),
     ("four_step.o", "four_step.cu", []),

@@ -261,6 +261,7 @@ struct Staging
     void* d_in[kSlots] = {nullptr, nullptr, nullptr};
     void* d_out[kSlots] = {nullptr, nullptr, nullptr};
     size_t in_cap = 0, out_cap = 0;
+    int in_slots = 0, out_slots = 0;           // buffers currently allocated (a single-chunk call allocates one pair)
     cudaStream_t stream[kSlots] = {nullptr, nullptr, nullptr};
 
     void release()
@@ -277,38 +278,55 @@ struct Staging
             stream[i] = nullptr;
         }
         in_cap = out_cap = 0;
+        in_slots = out_slots = 0;
         if (prev >= 0) cudaSetDevice(prev);
         device = -1;
     }
-    cudaError_t reserve(int dev, size_t in_bytes, size_t out_bytes)
+    // `slots` = chunks that will be in flight (a call with one chunk needs one pair of buffers, not three)
+    cudaError_t reserve(int dev, size_t in_bytes, size_t out_bytes, int slots)
     {
         if (device != dev) { release(); device = dev; }
         cudaError_t e;
         for (int i = 0; i < kSlots; ++i)
             if (!stream[i] && (e = cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
-        if (in_bytes > in_cap) {
-            for (int i = 0; i < kSlots; ++i) {
-                if (d_in[i]) cudaFree(d_in[i]);
-                d_in[i] = nullptr;
-                if ((e = cudaMalloc(&d_in[i], in_bytes)) != cudaSuccess) { in_cap = 0; return e; }
-            }
-            in_cap = in_bytes;
+        if ((e = grow(d_in, in_cap, in_slots, in_bytes, slots)) != cudaSuccess) return e;
+        if ((e = grow(d_out, out_cap, out_slots, out_bytes, slots)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
+    // one side's buffers: `slots` buffers of at least `bytes` each (growing the capacity reallocates all of them)
+    cudaError_t grow(void* (&buf)[kSlots], size_t& cap, int& have, size_t bytes, int slots)
+    {
+        if (bytes > cap) {
+            for (int i = 0; i < kSlots; ++i) { if (buf[i]) cudaFree(buf[i]); buf[i] = nullptr; }
+            cap = bytes;
+            have = 0;
         }
-        if (out_bytes > out_cap) {
-            for (int i = 0; i < kSlots; ++i) {
-                if (d_out[i]) cudaFree(d_out[i]);
-                d_out[i] = nullptr;
-                if ((e = cudaMalloc(&d_out[i], out_bytes)) != cudaSuccess) { out_cap = 0; return e; }
-            }
-            out_cap = out_bytes;
+        for (int i = have; i < slots; ++i) {
+            cudaError_t e = cudaMalloc(&buf[i], cap);
+            if (e != cudaSuccess) { buf[i] = nullptr; drop_buffers(); return e; }
+            have = i + 1;
         }
         return cudaSuccess;
+    }
+    // free the device buffers but keep the streams (after a call whose chunks were unusually large, or a failed reserve)
+    void drop_buffers()
+    {
+        for (int i = 0; i < kSlots; ++i) {
+            if (d_in[i]) cudaFree(d_in[i]);
+            if (d_out[i]) cudaFree(d_out[i]);
+            d_in[i] = d_out[i] = nullptr;
+        }
+        in_cap = out_cap = 0;
+        in_slots = out_slots = 0;
+        cudaGetLastError();
     }
     // A worker thread that exits gives its staging buffers back.  (At process teardown the runtime may already be
     // gone; the calls then fail harmlessly and the driver reclaims the memory.)
     ~Staging() { release(); cudaGetLastError(); }
 };
 thread_local Staging tl_staging;
+
+constexpr size_t kStagingKeepBytes = size_t(256) << 20;   // larger per-slot staging buffers are freed at the end of the call
 
 enum Side { SIDE_HOST, SIDE_DEVICE, SIDE_BAD };
 
@@ -385,8 +403,16 @@ int run_host(const _CkFftContext* c, Kind kind, int n, const void* in, void* out
     if (per_chunk > batch) per_chunk = batch;
     // device buffers are padded to 16 bytes so that every slot keeps 8-byte aligned transforms
     Staging& st = tl_staging;
-    cudaError_t e = st.reserve(c->device, per_chunk * ib + 16, per_chunk * ob + 16);
+    const size_t nchunks = (batch + per_chunk - 1) / per_chunk;
+    const int slots = nchunks < (size_t) Staging::kSlots ? (int) nchunks : Staging::kSlots;
+    cudaError_t e = st.reserve(c->device, per_chunk * ib + 16, per_chunk * ob + 16, slots);
     if (e != cudaSuccess) { set_error("staging allocation", e); return 0; }
+    // Staging stays with the thread for the next call -- unless one transform is so long that a single chunk pins
+    // hundreds of MiB of device memory (n >= 2^25): that is handed back when the call ends.
+    struct GiveBack {
+        Staging& st; bool on;
+        ~GiveBack() { if (on) st.drop_buffers(); }
+    } give_back{ st, per_chunk * ib > kStagingKeepBytes || per_chunk * ob > kStagingKeepBytes };
 
     size_t done = 0;
     int slot = 0;
@@ -405,7 +431,7 @@ int run_host(const _CkFftContext* c, Kind kind, int n, const void* in, void* out
             set_error("D2H copy", e); return 0;
         }
         done += cnt;
-        slot = (slot + 1) % Staging::kSlots;
+        slot = (slot + 1) % slots;
     }
     for (int i = 0; i < Staging::kSlots; ++i)
         if ((e = cudaStreamSynchronize(st.stream[i])) != cudaSuccess) { set_error("transform failed", e); return 0; }
@@ -484,6 +510,8 @@ int run_async(CkFftContext* c, Kind kind, int n, const void* in, void* out, size
 }  // namespace
 
 namespace ckb {
+void set_last_error(const char* text) { set_error(text); }      // multi.cu reports through the same channel
+
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count_of_current_device()
@@ -977,7 +1005,29 @@ CkFftB200DistPlan* CkFftB200DistPlanCreate(CkFftContext* c, long long n, int ran
     p->ctx = c;
     p->layout = lay;
     p->rank = rank;
-    p->epoch = 0;
+    // The flag block is caller-owned and may have served an earlier plan: a barrier passes when the slot has REACHED
+    // its epoch, so a new plan must continue from the value the block holds (every completed barrier leaves the same
+    // epoch in every slot of every rank), not from 0 -- otherwise its first barriers would all pass at once on the
+    // stale values and the passes would race.  The error word of an earlier time-out is cleared.
+    {
+        DeviceGuard guard(c->device);
+        unsigned words[CKB_MAX_PEERS + 1] = {0};
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaMemcpy(words, flags[rank], sizeof(words), cudaMemcpyDeviceToHost);
+        unsigned zero = 0;
+        if (e == cudaSuccess) e = cudaMemcpy((unsigned*) flags[rank] + CKB_MAX_PEERS, &zero, sizeof(zero), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { set_error("distributed plan: reading the flag block", e); free(p); return NULL; }
+        unsigned start = words[0];
+        for (int q = 1; q < world; ++q)
+            if ((int) (words[q] - start) > 0) start = words[q];
+        for (int q = 0; q < world; ++q)
+            if (words[q] != start) {
+                set_error("distributed plan: the flag block holds an unfinished barrier of an earlier plan (zero it on every rank, then rendezvous)");
+                free(p);
+                return NULL;
+            }
+        p->epoch = start;
+    }
     if (in) {
         // pull mode: tensor maps over every rank's input array, built once
         DeviceGuard guard(c->device);

@@ -144,34 +144,58 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const float4* __rest
 struct FlagPtrs { unsigned* f[CKB_MAX_PEERS]; };
 constexpr int kErrSlot = CKB_MAX_PEERS;
 
-__global__ void dist_barrier_kernel(FlagPtrs fl, int rank, int world, unsigned epoch)
+// `poison` (last barrier of an execution only): if this or an earlier barrier of the plan has timed out, the rank's
+// result is overwritten with NaNs so that a caller who never asks CkFftB200DistPlanStatus cannot mistake the garbage
+// for a spectrum.
+__global__ void __launch_bounds__(256) dist_barrier_kernel(FlagPtrs fl, int rank, int world, unsigned epoch, unsigned long long timeout_ns,
+                                                           float* poison, long long poison_floats)
 {
     const int q = threadIdx.x;
-    if (q >= world) return;
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(fl.f[q] + rank), "r"(epoch) : "memory");
-    const unsigned* mine = fl.f[rank] + q;
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (;;) {
-        unsigned v;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-        if ((int) (v - epoch) >= 0) break;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 20000000000ULL) {
-            fl.f[rank][kErrSlot] = 1u;
-            break;
+    if (q < world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(fl.f[q] + rank), "r"(epoch) : "memory");
+        const unsigned* mine = fl.f[rank] + q;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((int) (v - epoch) >= 0) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) {
+                fl.f[rank][kErrSlot] = 1u;
+                break;
+            }
+            __nanosleep(200);
         }
-        __nanosleep(200);
+        __threadfence_system();
     }
-    __threadfence_system();
+    if (poison == nullptr) return;
+    __syncthreads();
+    if (*reinterpret_cast<volatile unsigned*>(fl.f[rank] + kErrSlot) == 0u) return;
+    const float nan = __int_as_float(0x7fc00000);
+    for (long long i = threadIdx.x; i < poison_floats; i += blockDim.x) poison[i] = nan;
 }
 
-static cudaError_t launch_barrier(const DistBuffers& b, int rank, int world, unsigned epoch, cudaStream_t s)
+// Barrier timeout: 20 s by default (first-launch module loads, a debugger or an oversubscribed host can delay a peer
+// by seconds); CKFFT_B200_DIST_TIMEOUT_MS overrides it.
+static unsigned long long barrier_timeout_ns()
+{
+    static const unsigned long long ns = [] {
+        const char* e = getenv("CKFFT_B200_DIST_TIMEOUT_MS");
+        const long long ms = e && *e ? atoll(e) : 0;
+        return (unsigned long long) (ms > 0 ? ms : 20000) * 1000000ULL;
+    }();
+    return ns;
+}
+
+static cudaError_t launch_barrier(const DistBuffers& b, int rank, int world, unsigned epoch, cudaStream_t s,
+                                  cf* poison = nullptr, long long poison_elems = 0)
 {
     FlagPtrs fl{};
     for (int q = 0; q < world; ++q) fl.f[q] = b.flags[q];
-    dist_barrier_kernel<<<1, 32, 0, s>>>(fl, rank, world, epoch);
+    dist_barrier_kernel<<<1, poison ? 256 : 32, 0, s>>>(fl, rank, world, epoch, barrier_timeout_ns(), reinterpret_cast<float*>(poison),
+                                                        2 * poison_elems);
     count_launch();
     return cudaGetLastError();
 }
@@ -280,7 +304,8 @@ cudaError_t dist_exec(const CkFftB200DistLayout& l, int rank, const DistBuffers&
             e = launch_routed_pass(inverse, d.kind, d.L, p, s);
             mark(name);
             if (e == cudaSuccess && d.routed) {
-                e = launch_barrier(b, rank, l.world, ++*epoch, s);
+                const bool last = i == np - 1;          // the barrier that completes the execution also guards the result
+                e = launch_barrier(b, rank, l.world, ++*epoch, s, last ? b.buf[2][rank] : nullptr, last ? h * n2 : 0);
                 mark("barrier");
             }
         } else {

@@ -1,15 +1,21 @@
-"""Batch sharding for independent transforms: contiguous split of the batch over ranks,
-one process per GPU, no data-path collective.  Pure host logic (no GPU needed)."""
+"""Batch sharding for independent transforms: contiguous split of the batch over devices / ranks, no
+data-path collective.  The arithmetic lives in the library (`CkFftB200ShardRange`, csrc/multi.cu) -- it is what the
+multi-device scheduler behind `CkFft*BatchMulti` uses to cut a batch -- and this module is its Python mirror, so that
+a torchrun job (one process per GPU, bench.py) and the one-process scheduler shard a batch identically.
+Pure host logic (no GPU needed)."""
 from __future__ import annotations
+
+import ctypes as C
+
+from . import _lib
 
 
 def shard_range(batch: int, rank: int, world: int) -> tuple[int, int]:
     """[start, stop) of rank's contiguous shard; the first batch % world ranks get one extra transform."""
-    if world < 1 or not 0 <= rank < world:
+    first, count = C.c_size_t(0), C.c_size_t(0)
+    if batch < 0 or not _lib.load().CkFftB200ShardRange(int(batch), int(rank), int(world), C.byref(first), C.byref(count)):
         raise ValueError(f"bad rank/world {rank}/{world}")
-    base, extra = divmod(batch, world)
-    start = rank * base + min(rank, extra)
-    return start, start + base + (1 if rank < extra else 0)
+    return int(first.value), int(first.value + count.value)
 
 
 def all_shards(batch: int, world: int) -> list[tuple[int, int]]:

@@ -109,6 +109,41 @@ void CkFftB200HostFree(void* p);
 int CkFftB200ContextDevice(const CkFftContext* context);
 
 /*
+ * Batched scheduler: one host call spreads a batch of independent transforms over several GPUs of the box.
+ * The transforms of a batch share no state -- the reference says so itself ("the context does not contain state,
+ * so contexts can be used simultaneously on different threads", inc/ckfft/ckfft.h:39-41) -- so the batch is cut into
+ * contiguous shards (CkFftB200ShardRange), one per device; every device runs the ordinary host-buffer pipeline of the
+ * CkFft*Batch calls (chunked H2D -> kernel -> D2H, three chunks in flight) on its own streams from its own host
+ * thread, and the call returns when all shards are done.  There is no collective and no traffic between the GPUs.
+ *
+ *   CkFftB200MultiInit(nMax, direction, devices, nDevices)
+ *       one context replica (CkFftInit(nMax, direction) on that device) and one worker thread per entry of
+ *       devices[0 .. nDevices).  devices == NULL: the first nDevices visible devices (nDevices <= 0: all of them).
+ *       NULL on invalid arguments (the checks of CkFftInit, src/ckfft/ckfft.cpp:16-31), if a device does not exist or
+ *       if a replica cannot be created; CkFftB200LastError() says why.
+ *   CkFft{ComplexForward,ComplexInverse,RealForward,RealInverse}BatchMulti
+ *       the CkFft*Batch call of the same name on HOST arrays (pageable or pinned; dense strides), same checks and
+ *       1 / 0 return.  Calls that move >= 64 MiB page-lock pageable arrays for their duration (cudaHostRegister) so
+ *       that the copies of all devices run asynchronously; CKFFT_B200_MULTI_PIN=0 disables that.  One call at a time
+ *       per handle (concurrent callers are serialised).
+ *   CkFftB200MultiContext(m, i)  the replica on device i (for device-resident data: use it with the *BatchAsync calls)
+ *   CkFftB200ShardRange(batch, part, parts, &first, &count)
+ *       the shard of `part`: [first, first + count); the first batch % parts shards are one transform longer.
+ *       Pure host arithmetic (no GPU needed); returns 0 on bad arguments.
+ */
+typedef struct CkFftB200Multi CkFftB200Multi;
+CkFftB200Multi* CkFftB200MultiInit(int nMax, CkFftDirection direction, const int* devices, int nDevices);
+void CkFftB200MultiShutdown(CkFftB200Multi* multi);
+int CkFftB200MultiDeviceCount(const CkFftB200Multi* multi);
+int CkFftB200MultiDevice(const CkFftB200Multi* multi, int index);           /* CUDA device ordinal of replica `index`, or -1 */
+CkFftContext* CkFftB200MultiContext(const CkFftB200Multi* multi, int index);
+int CkFftB200ShardRange(size_t batch, int part, int parts, size_t* first, size_t* count);
+int CkFftComplexForwardBatchMulti(CkFftB200Multi* multi, int n, const CkFftComplex* input, CkFftComplex* output, size_t batch);
+int CkFftComplexInverseBatchMulti(CkFftB200Multi* multi, int n, const CkFftComplex* input, CkFftComplex* output, size_t batch);
+int CkFftRealForwardBatchMulti(CkFftB200Multi* multi, int n, const float* input, CkFftComplex* output, size_t batch);
+int CkFftRealInverseBatchMulti(CkFftB200Multi* multi, int n, const CkFftComplex* input, float* output, size_t batch);
+
+/*
  * Local steps of the distributed six-step transform of ONE very large 1-D FFT (n = n1*n2 spread over P GPUs,
  * ckfft_b200/distributed.py).  The exchange between GPUs (all-to-all) is the caller's, these are the
  * stream-ordered device kernels around it.  Device pointers, out of place unless noted.
@@ -197,14 +232,20 @@ typedef struct CkFftB200DistPlan CkFftB200DistPlan;
  * `in` (may be NULL): a fourth array of n/world complex per rank.  When given, the plan runs in PULL mode: there is no
  * exchange kernel, the first FFT pass fetches its tiles straight from the peers' `in` arrays with TMA; an execution
  * whose input is not the rank's own `in` array copies it there first.
- * The context must have been created with nMax >= n (it carries the twiddles of W_n). */
+ * The context must have been created with nMax >= n (it carries the twiddles of W_n).
+ * Flag blocks may be reused by a later plan on the same ranks (the new plan continues from the epoch the block holds)
+ * provided every execution of the earlier plan has completed on every rank; all ranks must rendezvous (application
+ * barrier) between creating their plans and the first execution. */
 CkFftB200DistPlan* CkFftB200DistPlanCreate(CkFftContext* context, long long n, int rank, int world, int preferPasses,
                                            void* const* work, void* const* mid, void* const* out, void* const* flags,
                                            void* const* in);
 /* Enqueue one transform of this rank's slice `input` (n/world complex, device memory, not one of the plan's
  * buffers) on `stream`.  inverse != 0: un-normalised inverse.  Returns 1 if everything was enqueued. */
 int CkFftB200DistExecAsync(CkFftB200DistPlan* plan, const CkFftComplex* input, int inverse, void* stream);
-/* Synchronises the device and returns 1 if no barrier of this plan has timed out so far, else 0. */
+/* Synchronises the device and returns 1 if no barrier of this plan has timed out so far, else 0.
+ * A barrier gives up after 20 s (CKFFT_B200_DIST_TIMEOUT_MS overrides) instead of hanging the GPU; the execution then
+ * carries on with incomplete data, ExecAsync has long returned 1, and the rank's `out` array is overwritten with NaNs
+ * by the execution's last barrier.  Call this after the executions whose results matter. */
 int CkFftB200DistPlanStatus(CkFftB200DistPlan* plan);
 /* Profiling: when on, every execution records an event after each of its kernels.  CkFftB200DistPlanPhases
  * synchronises and returns the number of phases of the LAST execution, their device times in ms[] (room for 12)

@@ -7,7 +7,8 @@ import sys
 import numpy as np
 import pytest
 
-from ckfft_b200.distributed import NumpyBackend, six_step, split_n
+from ckfft_b200.distributed import six_step, split_n
+from dist_replay import NumpyBackend
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -32,6 +33,7 @@ def test_single_rank_matches_fft():
 
 def _worker(rank, world, port, tmpdir):
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
 
     import oracle
@@ -114,7 +116,8 @@ def test_fused_layout_rules():
 def test_fused_replay_matches_fft(shape, inverse, pull):
     """All ranks simulated in one process: exchange (push layouts) or peer reads of the first pass (pull layouts) +
     the pass descriptors reproduce the N-point transform."""
-    from ckfft_b200.distributed import fused_layout, replay_fused
+    from ckfft_b200.distributed import fused_layout
+    from dist_replay import replay_fused
 
     la, lb, lc, ld, world = shape
     lay = fused_layout(la * lb * lc * ld, world) if min(lb, ld) >= 128 and la in (1,) and lc in (1, 128) else \
@@ -132,10 +135,12 @@ def test_fused_replay_matches_fft(shape, inverse, pull):
 
 def _fused_worker(rank, world, port, tmpdir):
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     import torch.distributed as dist
 
-    from ckfft_b200.distributed import fused_layout, replay_fused
+    from ckfft_b200.distributed import fused_layout
+    from dist_replay import replay_fused
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
