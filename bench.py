@@ -13,10 +13,18 @@ the data path); `value` is the work of all ranks divided by the slowest rank's d
 One JSON line on stdout (rank 0):
   value / ms_per_step   device-resident throughput, CUDA events on the launching stream, max over ranks
   e2e                   same metric through the C ABI with pinned HOST buffers (CkFftComplexForwardBatch:
-                        chunked H2D -> kernel -> D2H inside the timed region)
+                        chunked H2D -> kernel -> D2H inside the timed region), with its own roofline: the
+                        concurrent host<->device copy rate of this box measured in the same run (tools/pcie_peak.py)
+  e2e_pageable          the same call on malloc'ed (pageable) host arrays -- what a drop-in caller hands over
+  e2e_multi             the same work through ONE call of the multi-device scheduler (CkFftComplexForwardBatchMulti)
+                        from one process (rank 0) over all N GPUs
   roofline              algorithmic bytes / kernel time vs the measured HBM copy peak
   cpu_baseline          the reference ckfft (oracle/_ref, compiled unmodified) on this box's host cores
   clocks                nvidia-smi samples taken while the steps ran
+  secondary             the other BASELINE configs under the same clock: config 3 (R2C / C2R N=4096 x 2^18 frames),
+                        config 4 (size sweep N=2^4..2^20, batch = 2^28/N per GPU), large real transforms, and -- with
+                        N > 1 GPUs -- config 5 (one 2^30-point transform over the N GPUs, fused distributed path) with
+                        its phases, per-phase NVLink rate and an analytic + Parseval check
 `--impl reference` times the reference CPU implementation instead (rank 0 only), same metric/config.
 Other workloads (`--workload r2c4096|c2r4096|stft4096|c2c<N>|sweep|dist<log2N>`) exist for the parity configs, the size
 sweep and the distributed single transform (config 5);
@@ -71,6 +79,13 @@ def workload_spec(name: str):
             "c2r": f"batched real C2R N={n} x {batch} frames fp32 per GPU",
             "pow": f"Hann window + R2C + power spectrum N={n} x {batch} frames fp32 per GPU (fused)"}[kind]
     return dict(name=name, kind=kind, n=n, batch=batch, bytes=nbytes, flops=flops, desc=desc)
+
+
+def make_config(spec, world):
+    """the `config` object both arms print (the driver compares them)"""
+    return {"workload": spec["desc"], "n": spec["n"], "kind": spec["kind"], "batch_per_gpu": spec["batch"],
+            "bytes_per_transform": spec["bytes"], "l2": "inputs larger than L2 (no flush needed)",
+            "parallelism": f"batch-sharded x{world}, no collective"}
 
 
 def measured_peak():
@@ -256,10 +271,10 @@ def run_reference_arm(args, spec, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "gflops": round(spec["flops"] * sample / dt / 1e9, 2),
-        "config": {"workload": spec["desc"], "n": n, "kind": spec["kind"],
-                   "step": f"bounded sample: {sample} transforms per step on the host CPU"},
+        "config": make_config(spec, args.gpus),
         "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": cores, "kind": tag,
-                         "sample": f"{sample} transforms per step, OpenMP over the batch on {cores} host threads"},
+                         "sample": f"bounded sample of the workload: {sample} of {spec['batch']} transforms per step, OpenMP over "
+                                   f"the batch on {cores} host threads"},
         "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -267,113 +282,337 @@ def run_reference_arm(args, spec, rank):
 
 
 # ---------------------------------------------------------------------------------------------
-# config 4 of BASELINE.json: size sweep N = 2^4 .. 2^20, batch = 2^28 / N per GPU (2 GiB in + 2 GiB out)
+# device-timed building blocks (shared by the main line, `secondary` and the stand-alone workloads)
 # ---------------------------------------------------------------------------------------------
-def run_sweep(args, rank, world, local_rank, dev, barrier):
+def reduce_max(value, world, dev):
+    if world <= 1:
+        return float(value)
     import torch
     import torch.distributed as dist
 
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_sum(value, world, dev):
+    if world <= 1:
+        return float(value)
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def time_steps(step, steps, warmup, barrier, world, dev):
+    """mean ms per step: CUDA events on torch's current stream (the stream the library launches on), warm-up first,
+    barrier + synchronize on both sides, max over ranks"""
+    import torch
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    return reduce_max(e0.elapsed_time(e1) / steps, world, dev)
+
+
+def measure_sweep(world, dev, barrier, steps=5, lgs=range(4, 21)):
+    """BASELINE config 4: C2C forward, N = 2^4 .. 2^20, batch = 2^28 / N per GPU (2 GiB in + 2 GiB out per launch)."""
+    import torch
+
     import ckfft_b200 as ck
 
-    peak, peak_src = measured_peak()
+    peak, _ = measured_peak()
     total = 1 << 28
     x = torch.view_as_complex(torch.empty((total, 2), dtype=torch.float32, device=dev).uniform_(-1, 1))
     y = torch.empty_like(x)
     rows = []
-    steps = max(3, min(args.steps, 20))
-    for lg in range(4, 21):
+    for lg in lgs:
         n = 1 << lg
         ctx = ck.Context(n, ck.FORWARD)
         xv, yv = x.view(total // n, n), y.view(total // n, n)
-        for _ in range(3):
-            ctx.complex_forward(xv, yv)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            ctx.complex_forward(xv, yv)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1) / steps
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = time_steps(lambda: ctx.complex_forward(xv, yv), steps, 3, barrier, world, dev)
         gbs = 16.0 * total * world / ms / 1e6
-        rows.append({"n": n, "ms": round(ms, 4), "gbs": round(gbs, 1), "frac_per_gpu": round(gbs / world / peak, 4),
+        rows.append({"n": n, "ms": round(ms, 4), "gbs": round(gbs, 1), "frac": round(gbs / world / peak, 4),
                      "gflops": round(5.0 * total * lg * world / ms / 1e6, 1)})
         ctx.close()
+    del x, y
+    torch.cuda.empty_cache()
+    return rows
+
+
+def measure_real_large(world, dev, barrier, steps=5, lgs=range(17, 22)):
+    """real transforms beyond the single-pass limit (n = 2^17 .. 2^21, 2^27 samples per launch): R2C and C2R"""
+    import torch
+
+    import ckfft_b200 as ck
+
+    peak, _ = measured_peak()
+    total = 1 << 27
+    rows = []
+    for lg in lgs:
+        n = 1 << lg
+        batch = total // n
+        ctx = ck.Context(n, ck.BOTH)
+        xr = torch.empty((batch, n), dtype=torch.float32, device=dev).uniform_(-1, 1)
+        yc = torch.empty((batch, n // 2 + 1), dtype=torch.complex64, device=dev)
+        nbytes = (4 * n + 8 * (n // 2 + 1)) * batch
+        ms_f = time_steps(lambda: ctx.real_forward(xr, yc), steps, 3, barrier, world, dev)
+        ms_i = time_steps(lambda: ctx.real_inverse(yc, n, xr), steps, 3, barrier, world, dev)
+        rows.append({"n": n, "r2c_ms": round(ms_f, 4), "r2c_frac": round(nbytes / ms_f / 1e6 / peak, 4),
+                     "c2r_ms": round(ms_i, 4), "c2r_frac": round(nbytes / ms_i / 1e6 / peak, 4)})
+        ctx.close()
+        del xr, yc
+    torch.cuda.empty_cache()
+    return rows
+
+
+def measure_config3(name, world, dev, barrier, steps=20, warmup=5):
+    """BASELINE config 3 (and the fused audio front end): N = 4096 real, 2^18 frames per GPU"""
+    import torch
+
+    import ckfft_b200 as ck
+
+    spec = workload_spec(name)
+    n, batch, kind = spec["n"], spec["batch"], spec["kind"]
+    peak, _ = measured_peak()
+    ctx = ck.Context(n, ck.BOTH)
+    g = torch.Generator(device=dev).manual_seed(1235)
+    if kind == "c2r":
+        x = torch.view_as_complex(torch.empty((batch, n // 2 + 1, 2), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g))
+        y = torch.empty((batch, n), dtype=torch.float32, device=dev)
+        step = lambda: ctx.real_inverse(x, n, y)   # noqa: E731
+    else:
+        x = torch.empty((batch, n), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g)
+        if kind == "pow":
+            wnd = torch.hann_window(n, periodic=True, dtype=torch.float32, device=dev)
+            y = torch.empty((batch, n // 2 + 1), dtype=torch.float32, device=dev)
+            step = lambda: ctx.real_forward_power(x, wnd, y)   # noqa: E731
+        else:
+            y = torch.empty((batch, n // 2 + 1), dtype=torch.complex64, device=dev)
+            step = lambda: ctx.real_forward(x, y)   # noqa: E731
+    ms = time_steps(step, steps, warmup, barrier, world, dev)
+    gbs = spec["bytes"] * batch * world / ms / 1e6
+    ctx.close()
+    del x, y
+    torch.cuda.empty_cache()
+    return {"workload": spec["desc"], "value": round(gbs, 1), "unit": "GB/s", "ms_per_step": round(ms, 4), "steps": steps,
+            "frac": round(gbs / world / peak, 4), "gflops": round(spec["flops"] * batch * world / ms / 1e6, 1),
+            "bytes_per_transform": spec["bytes"]}
+
+
+def measure_dist(lg, rank, world, dev, barrier, steps=20, warmup=3):
+    """BASELINE config 5: ONE complex forward transform of N = 2^lg points spread over the GPUs of the box (strong
+    scaling) through the fused distributed path (peer stores / TMA reads over NVLink, no collective on the data path).
+    Timed on random data; checked on a closed-form signal (exponentials + an impulse) and by Parseval."""
+    import torch
+    import torch.distributed as dist
+
+    from ckfft_b200.distributed import FusedDistributedFFT
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from analytic import analytic_error, analytic_signal
+
+    n = 1 << lg
+    per = n // world
+    d = FusedDistributedFFT(n)
+    # ---- correctness first: closed-form spectrum, every bin of every rank ----
+    freqs, amps, n0 = [3, n // 3 + 1, n - 7], [1.0, 0.5, 0.25], 5
+    xa = analytic_signal(n, rank * per, per, dev, freqs, amps, n0)
+    if d.input is not None:
+        d.input.copy_(xa)
+        xa = d.input
+    ya = d.forward(xa)
+    d.check()
+    num, den = analytic_error(ya, n, rank * per, dev, freqs, amps, n0)
+    nd = torch.stack([num, den])
+    if world > 1:
+        dist.all_reduce(nd)
+    analytic_err = float(torch.sqrt(nd[0] / nd[1]).item())
+    del xa, ya
+    torch.cuda.empty_cache()
+    # ---- timing on random data ----
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.view_as_complex(torch.empty((per, 2), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g))
+    if d.input is not None:          # pull layouts: the input lives in the plan's peer-visible array (no local copy)
+        d.input.copy_(x)
+        x = d.input
+    out = {}
+    ms = time_steps(lambda: out.__setitem__("y", d.forward(x)), steps, warmup, barrier, world, dev)
+    d.check()
+    y = out["y"]
+    e = torch.stack([torch.linalg.vector_norm(x).double() ** 2, torch.linalg.vector_norm(y).double() ** 2 / n])
+    if world > 1:
+        dist.all_reduce(e)
+    parseval = abs(float(e[1] - e[0])) / float(e[0])
+    phases = d.profile(x)
+    barrier()
+    lay = d.layout
+    exch = d.bytes_per_exchange()
+    peak, peak_src = measured_peak()
+    per_gpu = 16.0 * n / world / ms / 1e6
+    tol = 1e-6 * lg
+    res = {
+        "workload": f"one complex forward FFT of 2^{lg} points over {world} GPU(s), fused distributed path",
+        "ms": round(ms, 4), "steps": steps, "value": round(16.0 * n / ms / 1e6, 1), "unit": "GB/s (algorithmic 16*N bytes / time, all GPUs)",
+        "gflops": round(5.0 * n * lg / ms / 1e6, 1),
+        "layout": f"n1 = {lay.la}x{lay.lb}, n2 = {lay.lc}x{lay.ld}, {lay.passes} passes, {'pull' if lay.pull else 'push'}",
+        "frac_hbm_per_gpu": round(per_gpu / peak, 4),
+        "exchange_bytes_per_gpu": exch,
+        "phases_ms": {f"{i}:{k}": round(v, 4) for i, (k, v) in enumerate(phases)},
+        # every phase whose kernel crosses NVLink moves (P-1)/P * 8N/P bytes out of (and into) each GPU
+        "nvlink_gbs": {f"{i}:{k}": round(exch / v / 1e6, 1) for i, (k, v) in enumerate(phases)
+                       if world > 1 and v > 0 and ("push" in k or "pull" in k or k == "exchange")},
+        "nvlink_floor_ms": round(3 * exch / 900e9 * 1e3, 4) if world > 1 else None,
+        "check": {"analytic_rel_rms": analytic_err, "parseval_rel": parseval, "tolerance": tol,
+                  "ok": bool(analytic_err <= tol and parseval <= 1e-5)},
+        "gpu_launches_per_step": len(phases),
+    }
+    d.close()
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_sweep(args, rank, world, local_rank, dev, barrier):
+    rows = measure_sweep(world, dev, barrier, steps=max(3, min(args.steps, 20)))
     if rank == 0:
+        peak, peak_src = measured_peak()
         mean = sum(r["gbs"] for r in rows) / len(rows)
         print(json.dumps({
             "metric": "Batched fp32 C2C FFT HBM GB/s, size sweep N=2^4..2^20 (mean over sizes)", "value": round(mean, 1), "unit": "GB/s",
-            "n_gpus": world, "steps": steps, "warmup": 3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "n_gpus": world, "steps": max(3, min(args.steps, 20)), "warmup": 3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "size sweep, batch = 2^28/N complex transforms per GPU (2 GiB in + 2 GiB out), forward",
                        "parallelism": f"batch-sharded x{world}, no collective", "peak": peak, "peak_source": peak_src},
             "sweep": rows}), flush=True)
 
 
+def run_dist(args, lg, rank, world, local_rank, dev, barrier):
+    res = measure_dist(lg, rank, world, dev, barrier, steps=min(args.steps, 50), warmup=max(3, min(args.warmup, 10)))
+    if rank == 0:
+        if not res["check"]["ok"]:
+            raise SystemExit(f"sanity check failed: {res['check']}")
+        peak, peak_src = measured_peak()
+        print(json.dumps({
+            "metric": f"single 1-D complex FFT N=2^{lg}, natural order in and out, algorithmic 16*N bytes / time", "value": res["value"],
+            "unit": "GB/s", "n_gpus": world, "steps": res["steps"], "warmup": max(3, min(args.warmup, 10)), "ms_per_step": res["ms"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "gflops": res["gflops"],
+            "config": {"workload": res["workload"], "layout": res["layout"], "l2": "inputs larger than L2",
+                       "parallelism": f"slices of N/{world}, peer stores over NVLink, 3 flag barriers, no collective"},
+            "roofline": {"bound": "hbm", "achieved": round(res["frac_hbm_per_gpu"] * peak, 1), "peak": peak, "unit": "GB/s",
+                         "frac": res["frac_hbm_per_gpu"], "traffic": None, "peak_source": peak_src,
+                         "note": "per GPU; the exchange phases are NVLink-bound (see phases_ms / nvlink_gbs)"},
+            "exchange_bytes_per_gpu": res["exchange_bytes_per_gpu"], "phases_ms": res["phases_ms"], "nvlink_gbs": res["nvlink_gbs"],
+            "check": res["check"], "gpu_launches": res["gpu_launches_per_step"] * res["steps"]}), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# end to end: the reference-facing call on HOST buffers
+# ---------------------------------------------------------------------------------------------
+def measure_e2e(args, spec, ctx, rank, world, local_rank, dev, barrier, host_barrier):
+    """-> (e2e, e2e_pageable, e2e_multi).  Wall clock around the synchronous C-ABI call, max over ranks."""
+    import torch
+
+    import ckfft_b200 as ck
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import pcie_peak
+
+    n, batch, kind = spec["n"], spec["batch"], spec["kind"]
+    in_shape = (batch, n) if kind != "c2r" else (batch, n // 2 + 1)
+    out_shape = (batch, n) if kind != "r2c" else (batch, n // 2 + 1)
+    in_dtype = torch.float32 if kind == "r2c" else torch.complex64
+    out_dtype = torch.float32 if kind == "c2r" else torch.complex64
+    hx = torch.empty(in_shape, dtype=in_dtype, pin_memory=True)
+    hy = torch.empty(out_shape, dtype=out_dtype, pin_memory=True)
+    torch.view_as_real(hx).uniform_(-1, 1) if hx.is_complex() else hx.uniform_(-1, 1)
+    nx, ny = hx.numpy(), hy.numpy()
+
+    def call(c, a, b):
+        if kind == "c2c":
+            return c.complex_forward(a, b)
+        if kind == "r2c":
+            return c.real_forward(a, b)
+        return c.real_inverse(a, n, b)
+
+    def timed(fn, steps):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        return reduce_max((time.perf_counter() - t0) / steps, world, dev)
+
+    in_bytes, out_bytes = int(hx.numel() * hx.element_size()), int(hy.numel() * hy.element_size())
+    # ---- pinned host arrays, one process per GPU ----
+    dt = timed(lambda: call(ctx, nx, ny), args.e2e_steps)
+    value = spec["bytes"] * batch * world / dt / 1e9
+    e2e = {"value": round(value, 2), "unit": "GB/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+           "ms_per_step": round(dt * 1e3, 3), "steps": args.e2e_steps,
+           "gflops": round(spec["flops"] * batch * world / dt / 1e9, 1),
+           "path": "CkFft*Batch on pinned host arrays: 32 MiB chunks, 3 in flight, H2D/kernel/D2H overlapped; "
+                   "wall clock around the synchronous call, max over ranks"}
+    # ---- pageable host arrays (what a drop-in caller's malloc gives): bounded sample of the same workload ----
+    sub = min(batch, 1 << 18)
+    px = np.empty((sub,) + tuple(in_shape[1:]), dtype=nx.dtype)
+    py = np.empty((sub,) + tuple(out_shape[1:]), dtype=ny.dtype)
+    px[...] = nx[:sub]
+    py[...] = 0
+    dtp = timed(lambda: call(ctx, px, py), 2)
+    pageable = {"value": round(spec["bytes"] * sub * world / dtp / 1e9, 2), "unit": "GB/s", "ms_per_step": round(dtp * 1e3, 3),
+                "sample": f"{sub} of {batch} transforms per GPU in numpy (malloc) arrays: the driver stages pageable copies, "
+                          "so H2D / D2H do not overlap",
+                "h2d_bytes_per_step": int(px.nbytes), "d2h_bytes_per_step": int(py.nbytes)}
+    same = bool(np.array_equal(py.view(np.uint32), ny[:sub].view(np.uint32)))
+    pageable["bit_identical_to_pinned_path"] = same
+    del px, py
+    # ---- one process, one call, all GPUs: the multi-device scheduler behind the C ABI (rank 0 drives, the others wait) ----
+    multi = None
+    host_barrier()
+    if rank == 0:
+        ndev = min(world, torch.cuda.device_count())
+        mc = ck.MultiContext(n, ck.BOTH, devices=list(range(ndev)))
+        fn = {"c2c": lambda: mc.complex_forward(nx, ny), "r2c": lambda: mc.real_forward(nx, ny),
+              "c2r": lambda: mc.real_inverse(nx, n, ny)}[kind]
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            fn()
+        dtm = (time.perf_counter() - t0) / args.e2e_steps
+        multi = {"value": round(spec["bytes"] * batch / dtm / 1e9, 2), "unit": "GB/s", "devices": mc.devices,
+                 "ms_per_step": round(dtm * 1e3, 3), "steps": args.e2e_steps, "transforms": batch,
+                 "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                 "path": f"CkFft*BatchMulti from ONE process: {batch} transforms in pinned host arrays sharded over {ndev} GPU(s) "
+                         "(strong scaling of one batch), one host thread + 3-slot H2D/kernel/D2H pipeline per device"}
+        mc.close()
+    host_barrier()
+    barrier()
+    # ---- the platform's copy ceiling, measured last (it overwrites the arrays): same pinned arrays, same chunking,
+    # every rank copying at once ----
+    link = pcie_peak.measure(local_rank, min(in_bytes, out_bytes, 4 << 30), 32 << 20, True, 2, hx, hy)
+    link_sum = reduce_sum(link["both"], world, dev)
+    e2e["roofline"] = {"bound": "host link (PCIe)", "achieved": e2e["value"], "peak": round(link_sum, 2), "unit": "GB/s",
+                       "frac": round(e2e["value"] / link_sum, 4),
+                       "peak_source": "plain cudaMemcpyAsync H2D + D2H at once on the same pinned arrays, 32 MiB chunks, "
+                                      f"all {world} GPU(s) copying concurrently, bytes of both directions / time (tools/pcie_peak.py)",
+                       "per_direction_gbs_rank0": {"h2d_alone": link["h2d"], "d2h_alone": link["d2h"], "both": link["both"]}}
+    barrier()
+    del hx, hy
+    return e2e, pageable, multi
+
+
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
-def run_dist(args, lg, rank, world, local_rank, dev, barrier):
-    """BASELINE config 5: ONE complex forward transform of N = 2^lg points spread over the GPUs of the box (strong
-    scaling), through the fused distributed path (peer stores over NVLink, no collective on the data path)."""
-    import torch
-    import torch.distributed as dist
-
-    from ckfft_b200.distributed import FusedDistributedFFT
-
-    n = 1 << lg
-    d = FusedDistributedFFT(n)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    x = torch.view_as_complex(torch.empty((n // world, 2), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=g))
-    if d.input is not None:          # pull layouts: the input lives in the plan's peer-visible array (no local copy)
-        d.input.copy_(x)
-        x = d.input
-    for _ in range(max(3, min(args.warmup, 10))):
-        d.forward(x)
-    barrier()
-    steps = min(args.steps, 50)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(steps):
-        y = d.forward(x)
-    ev1.record()
-    barrier()
-    d.check()
-    ms = torch.tensor([ev0.elapsed_time(ev1) / steps], dtype=torch.float64, device=dev)
-    e = torch.stack([torch.linalg.vector_norm(x).double() ** 2, torch.linalg.vector_norm(y).double() ** 2 / n])
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e)
-    phases = d.profile(x)
-    barrier()
-    if rank == 0:
-        ms = float(ms.item())
-        if not abs(float(e[1] - e[0])) <= 1e-5 * float(e[0]):
-            raise SystemExit("sanity check failed: Parseval")
-        lay = d.layout
-        peak, peak_src = measured_peak()
-        per_gpu = 16.0 * n / world / ms / 1e6
-        print(json.dumps({
-            "metric": f"single 1-D complex FFT N=2^{lg}, natural order in and out, algorithmic 16*N bytes / time", "value": round(16.0 * n / ms / 1e6, 1),
-            "unit": "GB/s", "n_gpus": world, "steps": steps, "warmup": max(3, min(args.warmup, 10)), "ms_per_step": round(ms, 4),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "gflops": round(5.0 * n * lg / ms / 1e6, 1),
-            "config": {"workload": f"one complex forward FFT of 2^{lg} points over {world} GPU(s), fused distributed path",
-                       "layout": f"n1 = {lay.la}x{lay.lb}, n2 = {lay.lc}x{lay.ld}, {lay.passes} passes", "l2": "inputs larger than L2",
-                       "parallelism": f"slices of N/{world}, peer stores over NVLink, 3 flag barriers, no collective"},
-            "roofline": {"bound": "hbm", "achieved": round(per_gpu, 1), "peak": peak, "unit": "GB/s", "frac": round(per_gpu / peak, 4),
-                         "traffic": None, "peak_source": peak_src,
-                         "note": "per GPU; the exchange phases are NVLink-bound (see phases_ms)"},
-            "exchange_bytes_per_gpu": d.bytes_per_exchange(),
-            "phases_ms": {f"{i}:{k}": round(v, 4) for i, (k, v) in enumerate(phases)},
-            "gpu_launches": len(phases) * steps}), flush=True)
-    d.close()
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -384,6 +623,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -413,6 +653,16 @@ def main():
         if world > 1:
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
+
+    # Host-side barrier (gloo: the waiting ranks block in a socket poll).  Used where rank 0 works alone for a while --
+    # the one-process multi-device call, the CPU baseline -- so that the other ranks neither keep a spinning NCCL
+    # kernel on their GPU nor burn a host core each while they wait.
+    host_group = dist.new_group(backend="gloo") if world > 1 else None
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=host_group)
 
     if args.workload == "sweep":
         run_sweep(args, rank, world, local_rank, dev, barrier)
@@ -458,11 +708,7 @@ def main():
     ev1.record()
     barrier()
     launches = ck.kernel_launches() - launches0
-    ms_total = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_total = reduce_max(ev0.elapsed_time(ev1), world, dev)
     ms_step = ms_total / args.steps
     if ms_total < 1000.0:
         # the timed region is shorter than a few sampling periods: keep the same step running (untimed) so that
@@ -483,47 +729,36 @@ def main():
         eout = float((yout.real.double() ** 2 + yout.imag.double() ** 2).sum()) / n
         if not abs(eout - ein) <= 1e-5 * ein:
             raise SystemExit(f"sanity check failed: Parseval {ein} vs {eout}")
+    del x, y
+    torch.cuda.empty_cache()
 
-    # ---- end to end through the C ABI with pinned host buffers ----
-    e2e = None
+    # ---- end to end through the C ABI with host buffers ----
+    e2e = pageable = multi = None
     if not args.no_e2e:
-        del x, y
-        torch.cuda.empty_cache()
-        in_shape = (batch, n) if kind != "c2r" else (batch, n // 2 + 1)
-        out_shape = (batch, n) if kind != "r2c" else (batch, n // 2 + 1)
-        in_dtype = torch.float32 if kind == "r2c" else torch.complex64
-        out_dtype = torch.float32 if kind == "c2r" else torch.complex64
-        hx = torch.empty(in_shape, dtype=in_dtype, pin_memory=True)
-        hy = torch.empty(out_shape, dtype=out_dtype, pin_memory=True)
-        torch.view_as_real(hx).uniform_(-1, 1) if hx.is_complex() else hx.uniform_(-1, 1)
-        nx, ny = hx.numpy(), hy.numpy()
-        if kind == "c2c":
-            host_step = lambda: ctx.complex_forward(nx, ny)   # noqa: E731
-        elif kind == "r2c":
-            host_step = lambda: ctx.real_forward(nx, ny)      # noqa: E731
-        else:
-            host_step = lambda: ctx.real_inverse(nx, n, ny)   # noqa: E731
-        host_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            host_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        dt /= args.e2e_steps
-        e2e = {"value": round(spec["bytes"] * batch * world / dt / 1e9, 2), "unit": "GB/s",
-               "h2d_bytes_per_step": int(hx.numel() * hx.element_size()),
-               "d2h_bytes_per_step": int(hy.numel() * hy.element_size()),
-               "ms_per_step": round(dt * 1e3, 3), "steps": args.e2e_steps,
-               "gflops": round(spec["flops"] * batch * world / dt / 1e9, 1),
-               "path": "CkFft*Batch on pinned host arrays: 32 MiB chunks, 3 in flight, H2D/kernel/D2H overlapped; "
-                       "wall clock around the synchronous call, max over ranks"}
-        del hx, hy
+        e2e, pageable, multi = measure_e2e(args, spec, ctx, rank, world, local_rank, dev, barrier, host_barrier)
 
+    # ---- the other BASELINE configs under the same clock ----
+    secondary = None
+    if not args.no_secondary and spec["name"] == "c2c1024":
+        secondary = {"note": "device-resident, CUDA events, max over ranks, same conventions as the main line; "
+                             "frac = per-GPU GB/s / measured HBM copy peak"}
+        secondary["r2c4096"] = measure_config3("r2c4096", world, dev, barrier)
+        secondary["c2r4096"] = measure_config3("c2r4096", world, dev, barrier)
+        secondary["stft4096"] = measure_config3("stft4096", world, dev, barrier)
+        sweep = measure_sweep(world, dev, barrier)
+        secondary["sweep"] = {"workload": "C2C forward, N = 2^4 .. 2^20, batch = 2^28/N per GPU, 5 steps each",
+                              "n": [r["n"] for r in sweep], "frac": [r["frac"] for r in sweep], "gbs": [r["gbs"] for r in sweep]}
+        real = measure_real_large(world, dev, barrier)
+        secondary["real_large"] = {"workload": "real n = 2^17 .. 2^21 (multi-pass), 2^27 samples per GPU per launch, 5 steps each",
+                                   "n": [r["n"] for r in real], "r2c_frac": [r["r2c_frac"] for r in real],
+                                   "c2r_frac": [r["c2r_frac"] for r in real]}
+        if world > 1:
+            try:
+                secondary["dist30"] = measure_dist(30, rank, world, dev, barrier, steps=20, warmup=3)
+            except Exception as exc:            # keep the main line: a failure here is reported, not fatal
+                secondary["dist30"] = {"error": f"{type(exc).__name__}: {exc}"}
+
+    host_barrier()
     if rank == 0:
         peak, peak_src = measured_peak()
         per_gpu = gbs / world
@@ -533,9 +768,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "gflops": round(gflops, 1), "gflops_convention": "5*N*log2(N) per complex transform (2.5*N*log2(N) real)",
-            "config": {"workload": spec["desc"], "n": n, "kind": kind, "batch_per_gpu": batch,
-                       "bytes_per_transform": spec["bytes"], "l2": "inputs larger than L2 (no flush needed)",
-                       "parallelism": f"batch-sharded x{world}, no collective"},
+            "config": make_config(spec, world),
             "roofline": {"bound": "hbm", "achieved": round(per_gpu, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(per_gpu / peak, 4), "traffic": ncu_traffic(spec["name"]),
                          "peak_source": peak_src,
@@ -546,11 +779,16 @@ def main():
         }
         if e2e is not None:
             line["e2e"] = e2e
-        if world == 1 and not args.no_cpu_baseline and kind != "pow":
+            line["e2e_pageable"] = pageable
+            line["e2e_multi"] = multi
+        if secondary is not None:
+            line["secondary"] = secondary
+        if not args.no_cpu_baseline and kind != "pow":
             line["cpu_baseline"] = cpu_baseline(spec)
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
+        host_barrier()
         dist.destroy_process_group()
 
 

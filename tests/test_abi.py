@@ -153,3 +153,24 @@ def test_no_gpu_fails_loudly():
     with pytest.raises(ck.CkFftError) as e:
         ck.Context(1024)
     assert "no CPU path" in str(e.value)
+
+
+def test_shard_range_and_multi_init_checks_need_no_gpu():
+    """CkFftB200ShardRange is pure host arithmetic; CkFftB200MultiInit validates its arguments like CkFftInit
+    (src/ckfft/ckfft.cpp:16-31) before it touches a device."""
+    lib = _lib.load()
+    first, count = C.c_size_t(0), C.c_size_t(0)
+    covered = 0
+    for part in range(5):
+        assert lib.CkFftB200ShardRange(13, part, 5, C.byref(first), C.byref(count)) == 1
+        assert first.value == covered and count.value in (2, 3)
+        covered += count.value
+    assert covered == 13
+    assert lib.CkFftB200ShardRange(13, 5, 5, C.byref(first), C.byref(count)) == 0
+    assert lib.CkFftB200ShardRange(13, 0, 0, C.byref(first), C.byref(count)) == 0
+    assert lib.CkFftB200ShardRange(13, 0, 2, None, C.byref(count)) == 0
+    assert not lib.CkFftB200MultiInit(1000, ck.BOTH, None, 0)
+    assert "power of two" in ck.last_error()
+    assert not lib.CkFftB200MultiInit(1024, 5, None, 0)
+    assert lib.CkFftB200MultiDeviceCount(None) == 0
+    lib.CkFftB200MultiShutdown(None)          # NULL-safe like CkFftShutdown (src/ckfft/ckfft.cpp:116-119)

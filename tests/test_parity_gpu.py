@@ -527,6 +527,129 @@ def test_fused_distributed_2_28_analytic(prefer, pull):
     torch.cuda.empty_cache()
 
 
+def test_fused_distributed_2_30_analytic():
+    """BASELINE config 5 at its named size on ONE GPU (world = 1: the routed kernels store into the GPU's own arrays, the
+    same kernels, barriers and layouts as across NVLink).  The reference cannot be the oracle here -- it cannot even
+    create a context for nMax >= 2^28 (src/ckfft/context.cpp:37-45) -- so the transform is checked against the
+    closed-form spectrum of exponentials + an impulse on every one of the 2^30 bins, by Parseval and by the round trip.
+    Needs ~50 GB of device memory (4 x 8 GiB plan arrays + the check's temporaries)."""
+    import os
+    import sys
+
+    from ckfft_b200.distributed import FusedDistributedFFT
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from analytic import analytic_error, analytic_signal
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < (56 << 30):
+        pytest.skip("needs 56 GiB of free device memory")
+    n = 1 << 30
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d = FusedDistributedFFT(n)                   # default layout for 2^30: four passes, pull
+    assert d.layout.passes == 4 and d.input is not None
+    freqs, amps, n0 = [3, n // 3 + 1, n - 7], [1.0, 0.5, 0.25], 5
+    d.input.copy_(analytic_signal(n, 0, n, dev, freqs, amps, n0))
+    torch.cuda.empty_cache()
+    x = d.input
+    ex = float(torch.linalg.vector_norm(x).double() ** 2)
+    y = d.forward(x)
+    d.check()
+    num, den = analytic_error(y, n, 0, dev, freqs, amps, n0)
+    assert float(torch.sqrt(num / den)) <= tolerance(n)
+    ey = float(torch.linalg.vector_norm(y).double() ** 2) / n
+    assert abs(ey - ex) <= 1e-5 * ex                                  # Parseval
+    spot = y[[0, 3, n // 3 + 1, n - 7, n // 2]].cpu().numpy()        # the three spectral lines stand n * a_i above the impulse's unit circle
+    assert abs(abs(spot[1]) - n) <= 2 and abs(abs(spot[2]) - n / 2) <= 2 and abs(abs(spot[3]) - n / 4) <= 2
+    # round trip: inverse(forward(x)) = n * x.  The inverse reads `out` through a copy into the pull array.
+    keep = x[: 1 << 20].clone()
+    z = d.inverse(y.clone())
+    d.check()
+    err = float(torch.linalg.vector_norm(z[: 1 << 20] / n - keep) / torch.linalg.vector_norm(keep))
+    assert err <= tolerance(n)
+    d.close()
+    torch.cuda.empty_cache()
+
+
+def test_fused_distributed_flag_block_serves_a_second_plan():
+    """A C caller may destroy a plan and create another one on the same work / mid / out / flag buffers:
+    the new plan must continue from the epoch the flag block holds, otherwise its barriers pass at once on stale values."""
+    from ckfft_b200.distributed import FusedDistributedFFT
+
+    lib = _lib.load()
+    n = 1 << 22
+    rng = np.random.default_rng(22)
+    x = uniform_complex(rng, (n,))
+    want = oracle.fp64_c2c(x)
+    xd = torch.from_numpy(x).cuda()
+    d = FusedDistributedFFT(n, pull=False)
+    for _ in range(3):
+        d.forward(xd)
+    d.check()
+    arrs = [(C.c_void_p * 1)(d._own[b]) for b in range(4)]
+    for prefer in (3, 0):
+        plan2 = lib.CkFftB200DistPlanCreate(d.ctx.handle, n, 0, 1, prefer, arrs[0], arrs[1], arrs[2], arrs[3], None)
+        assert plan2, ck.last_error()
+        assert lib.CkFftB200DistExecAsync(plan2, xd.data_ptr(), 0, torch.cuda.current_stream().cuda_stream) == 1
+        assert lib.CkFftB200DistPlanStatus(plan2) == 1
+        assert rel_rms(d.out.cpu().numpy(), want) <= tolerance(n)
+        lib.CkFftB200DistPlanDestroy(plan2)
+    d.close()
+
+
+def test_single_chunk_host_call_allocates_one_staging_pair():
+    """a host call that fits one chunk needs one pair of staging buffers, not three, and staging larger
+    than 256 MiB per slot is handed back when the call ends."""
+    import threading
+
+    n = 1 << 24                                   # one transform = 128 MiB in + 128 MiB out = one chunk
+    rng = np.random.default_rng(3)
+    x = uniform_complex(rng, (n,))
+    result = {}
+
+    def work():                                   # a fresh thread: fresh per-thread staging
+        with ck.Context(n, ck.FORWARD) as ctx:
+            torch.cuda.synchronize()
+            free0, _ = torch.cuda.mem_get_info()
+            y = ctx.complex_forward(x)
+            free1, _ = torch.cuda.mem_get_info()
+            result["grew"] = free0 - free1
+            result["y"] = y
+
+    t = threading.Thread(target=work)
+    t.start()
+    t.join()
+    assert rel_rms(result["y"], oracle.fp64_c2c(x)) <= tolerance(n)
+    assert result["grew"] <= (320 << 20), result["grew"]        # one pair (256 MiB + slack), not three (768 MiB)
+
+
+def test_out_arguments_are_validated(ctx_big):
+    """a caller-supplied `out` travels to the C ABI as a bare pointer -- wrong dtype / shape / layout /
+    side must raise instead of writing out of bounds."""
+    x = uniform_complex(np.random.default_rng(0), (4, 256))
+    xd = torch.from_numpy(x).cuda()
+    good = np.empty_like(x)
+    assert ctx_big.complex_forward(x, good) is good
+    for bad in (np.empty((4, 255), np.complex64), np.empty((4, 256), np.complex128), np.empty((256, 4), np.complex64).T,
+                np.empty((3, 256), np.complex64), torch.empty((4, 256), dtype=torch.complex64, device="cuda")):
+        with pytest.raises(ck.CkFftError):
+            ctx_big.complex_forward(x, bad)
+    for bad in (torch.empty((4, 256), dtype=torch.complex64), torch.empty((4, 512), dtype=torch.complex64, device="cuda")[:, ::2],
+                torch.empty((4, 256), dtype=torch.float32, device="cuda"), good):
+        with pytest.raises(ck.CkFftError):
+            ctx_big.complex_forward(xd, bad)
+    xr = np.zeros((2, 64), np.float32)
+    with pytest.raises(ck.CkFftError):
+        ctx_big.real_forward(xr, np.empty((2, 32), np.complex64))               # n/2 + 1 = 33 bins
+    with pytest.raises(ck.CkFftError):
+        ctx_big.real_inverse(np.zeros((2, 33), np.complex64), 64, np.empty((2, 63), np.float32))
+    with pytest.raises(ck.CkFftError):
+        ctx_big.real_forward_power(torch.zeros((2, 64), device="cuda"), None, torch.empty((2, 33), dtype=torch.float64, device="cuda"))
+    re = torch.zeros((2, 64), device="cuda")
+    with pytest.raises(ck.CkFftError):
+        ctx_big.complex_planar(re, re.clone(), False, (torch.empty((2, 64), device="cuda"), torch.empty((2, 32), device="cuda")))
+
+
 def test_fused_distributed_rejects_bad_arguments():
     from ckfft_b200.distributed import FusedDistributedFFT
 
