@@ -14,11 +14,18 @@
 //     __threadfence + atomicAdd, acquired by the thread that issues the pass-2 bulk copies, followed by a
 //     generic->async proxy fence) and done2[p] (pass-2 tiles whose copies have landed in shared memory, which frees
 //     the ring slot for problem p + RING);
-//   * warp specialisation: 8 consumer warps do the arithmetic; a 9th (producer) warp draws the ticket of the NEXT
-//     item, polls its dependencies, requests its tile from the TMA unit as soon as the consumers have drained the
-//     buffer (mbarrier `free`), and raises the completion counter of the finished item once the consumers have issued
-//     their stores (mbarrier `stored`): no global round trip sits on the consumers' path, and they synchronise among
-//     themselves only twice per item (named barrier).
+//   * warp specialisation: 8 consumer warps do the arithmetic; a *loader* thread draws the ticket of the NEXT item,
+//     polls its dependencies and requests its tile from the TMA unit as soon as the consumers have drained the
+//     buffer (mbarrier `free`); a *signaller* thread raises the completion counter of a finished item once the
+//     consumers have issued their stores (mbarrier ring `stored`): no global round trip sits on the consumers' path,
+//     and they synchronise among themselves only twice per item (named barrier).
+//   * the service threads never invalidate the SM's L1: dependency polls are `ld.relaxed.gpu` (the data they guard is
+//     read by the async proxy, i.e. from L2, after a proxy fence) and the completion counter is raised with
+//     `red.release.gpu` instead of __threadfence + atomicAdd.  ptxas puts a CCTL.IVALL behind every gpu-scope ACQUIRE
+//     (ld.acquire, fence.sc / acq_rel): round 1 did one per poll and per signalled item, i.e. the L1 of every SM was
+//     flushed about once a microsecond and the consumers' inter-pass twiddle loads went to L2 every time.
+//   * every wait inside the CTA is a blocking mbarrier try_wait (the hardware suspends the thread), every global spin
+//     has a watchdog (globaltimer) that traps instead of hanging the GPU.
 // The arithmetic of a tile is exactly that of tile_kernel (same stage functions, same twiddle factorisation), so
 // results are bit-identical to the two-kernel path.
 #pragma once
@@ -47,12 +54,48 @@ struct PipeParams {
     int tw_shift_real;      // scales an exponent of W_(2M) to one of W_Tmax
 };
 
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p)
+// gpu-scope poll that does not touch the L1 (no CCTL.IVALL behind it, unlike ld.acquire.gpu): the value comes from L2
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p)
 {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+
+// counter += 1 with release semantics at gpu scope: everything this thread has observed (the consumers' stores, through
+// the `stored` mbarrier) is visible to whoever reads the new value.  A release needs no L1 invalidation.
+__device__ __forceinline__ void red_release_gpu_inc(unsigned* p)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// blocking wait with a suspend-time hint: the hardware parks the thread until the phase completes (or ~the hint
+// elapses), so a waiting service thread costs no issue slots.  Bounded: a protocol bug traps instead of hanging.
+constexpr unsigned long long kPipeWatchdogNs = 10000000000ULL;      // a wait that does not resolve in 10 s is a bug
+
+__device__ __forceinline__ void mbar_wait_parked(unsigned long long* bar, unsigned parity)
+{
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0;; ++spins) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+        if (ok) return;
+        if ((spins & 63u) == 63u) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kPipeWatchdogNs) __trap();
+        }
+    }
+}
+
 
 __device__ __forceinline__ unsigned long long l2_evict_normal_policy()
 {
@@ -96,7 +139,7 @@ struct PipeCfg {
     static constexpr int XA = A::C * A::XBUF, XB = B::C * B::XBUF;
     static constexpr int XALL = ((XA > XB ? XA : XB) + 15) & ~15;   // whole 128-byte lines
     static constexpr int LUTA = A::LUT1, LUTB = B::LUT1;
-    static constexpr int SMEM_BYTES = 8 * (LUTA + LUTB + NBUF * XALL) + 64;
+    static constexpr int SMEM_BYTES = 8 * (LUTA + LUTB + NBUF * XALL) + 128;
     static_assert((XALL * 8) % 128 == 0, "tile buffer alignment");
     static_assert(((LUTA + LUTB) * 8) % 128 == 0, "tile buffer alignment");
 };
@@ -115,10 +158,12 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
     cf* lutB = lutA + PC::LUTA;
     cf* xall = lutB + PC::LUTB;
     constexpr int NBUF = PC::NBUF;
+    // control block (128 bytes behind the tile buffers)
     unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(xall + NBUF * PC::XALL);   // [2] tile landed (TMA complete_tx)
     unsigned long long* bar_free = bar_full + 2;       // [2] every consumer has drained the buffer (stage-1 gather done)
-    unsigned long long* bar_stored = bar_full + 4;     // every consumer has issued its global stores of the item
-    unsigned* item_slot = reinterpret_cast<unsigned*>(bar_full + 5);                         // [4]: ticket of item k at k & 3
+    unsigned long long* bar_stored = bar_full + 4;     // [4] ring: every consumer has issued its global stores of item k (k & 3)
+    unsigned long long* bar_sig = bar_full + 8;        // [4] ring: the signaller has handled item k (k & 3)
+    unsigned* item_slot = reinterpret_cast<unsigned*>(bar_full + 12);                        // [8]: ticket of item k at k & 7
     const int tid = threadIdx.x;
 
     {
@@ -127,13 +172,11 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
         for (int i = tid; i < PC::LUTB; i += THREADS + 64) lutB[i] = table_w(p.table, ((i / B::R0 + 1) * (i % B::R0)) << shB, INV);
     }
     if (tid == 0) {
-        item_slot[4] = 0u;
-        item_slot[5] = 0xffffffffu;
         mbar_init(bar_full, 1);
         mbar_init(bar_full + 1, 1);
         mbar_init(bar_free, THREADS);
         mbar_init(bar_free + 1, THREADS);
-        mbar_init(bar_stored, THREADS);
+        for (int i = 0; i < 4; ++i) { mbar_init(bar_stored + i, THREADS); mbar_init(bar_sig + i, 1); }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -170,51 +213,54 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
     };
 
     if (tid >= THREADS) {
-        // ---------------- two service warps (one lane each): loader and signaller ----------------
-        // No global round trip (ticket atomic, dependency poll, the fence before a completion counter) sits on the
+        // ---------------- two service threads (lane 0 of two warps): loader and signaller ----------------
+        // No global round trip (ticket atomic, dependency poll, the release of a completion counter) sits on the
         // consumers' critical path, and the two chains do not serialise each other: the loader draws the next ticket
-        // and polls its dependencies while the consumers work, then requests the tile the moment the buffer is free;
+        // and polls its dependencies while the consumers work, then requests the tile the moment a buffer is free;
         // the signaller raises done1 once the consumers have issued an item's stores.  Only the loader ever waits for
         // other CTAs, and never for anything this CTA still has to signal (that is the signaller's job), so the
         // ticket-order argument for deadlock freedom is unchanged.
-        volatile unsigned* sig_count = item_slot + 4;      // items whose completion the signaller has handled
-        volatile unsigned* last_item = item_slot + 5;      // index of the sentinel item once the loader has drawn it
+        // Item k of this CTA uses tile buffer k % NBUF, `stored` / `sig` barrier k & 3 and ticket slot k & 7.  The loader
+        // requests item j only after the signaller has handled item j - 4 (bar_sig), which keeps every barrier of the two
+        // rings within one phase of its waiter and every ticket slot alive until the signaller has read it.
         if (tid == THREADS + 32) {
             for (unsigned k = 0;; ++k) {                                   // signaller
-                while (!mbar_try_wait(bar_stored, k & 1u)) {
-                    if (k >= *last_item) return;                           // the consumers never run the sentinel
-                    __nanosleep(100);
-                }
+                mbar_wait_parked(bar_stored + (k & 3u), (k >> 2) & 1u);
+                const unsigned long long t = item_slot[k & 7u];
+                if (t >= total) return;                                    // sentinel (the consumers arrive for it, too)
                 int pass; long long prob; int c0;
-                decode(item_slot[k & 3u], pass, prob, c0);
-                if (pass == 1) {
-                    __threadfence();                                       // the consumers' stores, ordered at gpu scope before the counter
-                    atomicAdd(p.done1 + prob, 1u);
-                }
-                *sig_count = k + 1;
+                decode(t, pass, prob, c0);
+                if (pass == 1) red_release_gpu_inc(p.done1 + prob);        // the consumers' stores are visible before the count
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_sig + (k & 3u))) : "memory");
             }
         }
         if (tid != THREADS) return;
         const unsigned long long pol_stream = l2_evict_first_policy();
         const unsigned long long pol_keep = l2_evict_normal_policy();
+        auto spin_until = [&](const unsigned* ctr, unsigned want) {
+            if (ld_relaxed_gpu(ctr) >= want) return;
+            const unsigned long long t0 = global_timer_ns();
+            while (ld_relaxed_gpu(ctr) < want) {
+                __nanosleep(200);
+                if (global_timer_ns() - t0 > kPipeWatchdogNs) __trap();
+            }
+        };
         auto wait_deps = [&](unsigned long long t) {
             if (t >= total) return;
             int pass; long long prob; int c0;
             decode(t, pass, prob, c0);
             if (pass == 1) {
-                if (prob >= p.ring_slots)
-                    while (ld_acquire_gpu(p.done2 + (prob - p.ring_slots)) < (unsigned) T2) __nanosleep(100);
+                if (prob >= p.ring_slots) spin_until(p.done2 + (prob - p.ring_slots), (unsigned) T2);
             } else {
-                while (ld_acquire_gpu(p.done1 + prob) < (unsigned) T1) __nanosleep(100);
+                spin_until(p.done1 + prob, (unsigned) T1);
             }
         };
         auto request = [&](unsigned long long t, unsigned k) {        // item number k of this CTA carries ticket t
-            item_slot[k & 3u] = (unsigned) t;
+            item_slot[k & 7u] = (unsigned) (t < total ? t : total);
             const unsigned b = k % NBUF;
             cf* stage = xall + b * PC::XALL;
             unsigned long long* full = bar_full + b;
             if (t >= total) {                                          // sentinel: complete the phase without a copy
-                *last_item = k;
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(full)) : "memory");
                 return;
             }
@@ -234,16 +280,11 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
                 for (int g = 0; g < B::C; ++g) bulk_load(stage + g * L1, slot + (long long) pass2_column(c0, g) * L1, L1 * 8, full, pol_keep);
             }
         };
-        // item j goes into buffer j % NBUF, which item j - NBUF must have drained; the signaller is kept within one item
-        // (sig_count >= j - 1 before request j), which bounds the phase distance on `stored` and the reuse of item_slot
         for (unsigned j = 0;; ++j) {
             const unsigned long long t = atomicAdd(p.ticket, 1u);
             wait_deps(t);
-            if (j >= (unsigned) NBUF) {
-                const unsigned use = j / NBUF - 1;                                 // completion number of that buffer's barrier
-                while (!mbar_try_wait(bar_free + j % NBUF, use & 1u)) __nanosleep(40);
-            }
-            if (j >= 2) while (*sig_count + 1 < j) __nanosleep(40);
+            if (j >= (unsigned) NBUF) mbar_wait_parked(bar_free + j % NBUF, (j / NBUF - 1) & 1u);     // item j - NBUF has drained the buffer
+            if (j >= 4u) mbar_wait_parked(bar_sig + (j & 3u), ((j >> 2) - 1) & 1u);                  // item j - 4 has been signalled
             request(t, j);
             if (t >= total) return;
         }
@@ -255,9 +296,12 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
         const unsigned b = k % NBUF;
         cf* xb = xall + b * PC::XALL;                           // this item's buffer: staged tile first, exchange buffer after
         unsigned long long* bfree = bar_free + b;
-        mbar_wait(bar_full + b, (k / NBUF) & 1u);
-        const unsigned long long cur = item_slot[k & 3u];
-        if (cur >= total) break;
+        mbar_wait_parked(bar_full + b, (k / NBUF) & 1u);
+        const unsigned long long cur = item_slot[k & 7u];
+        if (cur >= total) {                                     // sentinel: tell the signaller, then leave
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_stored + (k & 3u))) : "memory");
+            break;
+        }
         int pass; long long prob; int c0;
         decode(cur, pass, prob, c0);
         if (pass == 1) {
@@ -380,7 +424,7 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bfree)) : "memory");
             }
         }
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_stored)) : "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_stored + (k & 3u))) : "memory");
     }
 }
 
