@@ -50,6 +50,14 @@ UNITS = [
 ]
 
 
+# CKFFT_B200_UNIT_FLAGS="four_step.o:-DX=1 -DY=2;api.o:-DZ" adds flags to single translation units (development A/B builds)
+_UNIT_FLAGS = {}
+for _item in os.environ.get("CKFFT_B200_UNIT_FLAGS", "").split(";"):
+    if ":" in _item:
+        _obj, _fl = _item.split(":", 1)
+        _UNIT_FLAGS[_obj.strip()] = _fl.split()
+
+
 def _source_stamp() -> str:
     h = hashlib.sha256()
     for d in (CSRC, os.path.join(ROOT, "include", "ckfft")):
@@ -58,6 +66,8 @@ def _source_stamp() -> str:
                 h.update(name.encode())
                 h.update(f.read())
     h.update(" ".join(COMMON).encode())
+    h.update(repr(sorted(_UNIT_FLAGS.items())).encode())
+    h.update(repr(UNITS).encode())
     return h.hexdigest()
 
 
@@ -83,7 +93,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_unit(unit):
         obj, src, extra = unit
-        cmd = [NVCC, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", os.path.join(OBJ, obj)]
+        cmd = [NVCC, *COMMON, *extra, *_UNIT_FLAGS.get(obj, []), "-c", os.path.join(CSRC, src), "-o", os.path.join(OBJ, obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         out = _run(cmd)

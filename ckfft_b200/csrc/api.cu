@@ -98,7 +98,7 @@ cudaError_t enqueue(const _CkFftContext* c, Kind kind, int n, const void* in, vo
                     long long in_stride, long long out_stride, cudaStream_t s);
 
 // ---- multi-pass lengths ---------------------------------------------------------------------
-// Scratch is stream-ordered (cudaMallocAsync / cudaFreeAsync): nothing mutable lives in the context.
+// Scratch is stream-ordered (ckb::scratch_alloc = the library's own memory pool / cudaFreeAsync): nothing mutable lives in the context.
 constexpr size_t kScratchCapBytes = size_t(2) << 30;      // real-transform glue buffers
 
 // Group size of the multi-pass transforms = size of the stream-ordered scratch array.  Measured on B200: groups
@@ -143,7 +143,7 @@ cudaError_t enqueue_large_c2c(const _CkFftContext* c, bool inv, int n, const ckb
     if (sub < 1) sub = 1;
     if (sub > batch) sub = batch;
     ckb::cf* scratch = nullptr;
-    cudaError_t e = cudaMallocAsync((void**) &scratch, per * (size_t) sub, s);
+    cudaError_t e = ckb::scratch_alloc((void**) &scratch, per * (size_t) sub, s);
     if (e != cudaSuccess) return e;
     for (long long done = 0; done < batch && e == cudaSuccess; done += sub) {
         const long long cnt = batch - done < sub ? batch - done : sub;
@@ -174,12 +174,23 @@ cudaError_t enqueue_large_real(const _CkFftContext* c, bool inverse, int n, cons
         }
         return e;
     }
+    if (inverse && M <= (1 << 20) && ckb::pipe_enabled() && getenv_flag("CKFFT_B200_PIPE_REAL", 1)) {
+        // real inverse: twist + half-length complex transform in ONE dataflow kernel (pipe_kernel.cuh, PipeCfg::TWIST)
+        const long long chunk = 1LL << 20;
+        cudaError_t e = cudaSuccess;
+        for (long long done = 0; done < batch && e == cudaSuccess; done += chunk) {
+            const long long cnt = batch - done < chunk ? batch - done : chunk;
+            e = ckb::launch_pipe_c2r(ilog2i(M), (const cf*) in + done * (M + 1), (cf*) ((float*) out + done * n), cnt, M + 1,
+                                     c->dTable, c->log2Table, big_tw(c), s);
+        }
+        return e;
+    }
     const size_t per = (size_t) M * sizeof(cf);
     long long sub = (long long) (kScratchCapBytes / per);
     if (sub < 1) sub = 1;
     if (sub > batch) sub = batch;
     cf* half = nullptr;      // Z (forward) or T (inverse): M complex per frame
-    cudaError_t e = cudaMallocAsync((void**) &half, per * (size_t) sub, s);
+    cudaError_t e = ckb::scratch_alloc((void**) &half, per * (size_t) sub, s);
     if (e != cudaSuccess) return e;
     for (long long done = 0; done < batch && e == cudaSuccess; done += sub) {
         const long long cnt = batch - done < sub ? batch - done : sub;
@@ -387,12 +398,38 @@ int run_host_small(const _CkFftContext* c, Kind kind, int n, const void* in, voi
     return 1;
 }
 
+// Pageable host arrays: cudaMemcpyAsync on them is staged through the driver's bounce buffers and is synchronous, so
+// nothing overlaps (measured: 7 GB/s end to end against 75-95 GB/s for pinned arrays).  A call that moves at least
+// kPinThresholdBytes therefore page-locks the caller's arrays for its duration (cudaHostRegister) -- what a drop-in
+// caller's malloc'ed buffers need to reach the copy engines at full rate.  CKFFT_B200_PIN=0 disables it.
+constexpr size_t kPinThresholdBytes = size_t(64) << 20;
+
+struct ScopedPin
+{
+    void* p = nullptr;
+    ScopedPin(const void* ptr, size_t bytes, bool read_only)
+    {
+        if (bytes == 0) return;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return; }
+        if (a.type != cudaMemoryTypeUnregistered) return;                       // already pinned (or not plain host memory)
+        cudaError_t e = cudaErrorUnknown;
+        if (read_only) e = cudaHostRegister((void*) ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly);
+        if (e != cudaSuccess) { cudaGetLastError(); e = cudaHostRegister((void*) ptr, bytes, cudaHostRegisterPortable); }
+        if (e == cudaSuccess) p = (void*) ptr;
+        else cudaGetLastError();                                                // refused: the copies simply stay synchronous
+    }
+    ~ScopedPin() { if (p) { cudaHostUnregister(p); cudaGetLastError(); } }
+};
+
 // Host arrays: stream the batch through the GPU in chunks, three in flight
 // (H2D of chunk i+1, kernel of chunk i and D2H of chunk i-1 overlap on separate streams).
 int run_host(const _CkFftContext* c, Kind kind, int n, const void* in, void* out, size_t batch)
 {
     const size_t ib = in_elems(kind, n) * in_elem_bytes(kind);     // bytes per transform
     const size_t ob = out_elems(kind, n) * out_elem_bytes(kind);
+    const bool pin = (ib + ob) * batch >= kPinThresholdBytes && getenv_flag("CKFFT_B200_PIN", 1);
+    ScopedPin pin_in(in, pin ? ib * batch : 0, true), pin_out(out, pin ? ob * batch : 0, false);
     static const size_t target = [] {                              // input bytes per chunk (default 32 MiB)
         const char* e = getenv("CKFFT_B200_CHUNK_MB");
         const long mb = e ? atol(e) : 0;
@@ -511,6 +548,49 @@ int run_async(CkFftContext* c, Kind kind, int n, const void* in, void* out, size
 
 namespace ckb {
 void set_last_error(const char* text) { set_error(text); }      // multi.cu reports through the same channel
+
+// Stream-ordered scratch from the library's OWN memory pool (one per device).  The default pool of cudaMallocAsync
+// gives unused memory back to the driver at every synchronisation (release threshold 0), so a caller who synchronises
+// between calls -- every classic CkFft* call does -- paid a fresh cudaMalloc of the multi-pass scratch (64 MiB .. 2 GiB)
+// on every call: measured 2 x the kernel time for real n = 2^17 .. 2^21.  The private pool keeps up to
+// CKFFT_B200_POOL_KEEP_MB (default 2304) MiB between calls and touches nobody else's allocator settings.
+cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t s)
+{
+    static cudaMemPool_t pools[64] = {nullptr};
+    static std::atomic<int> state[64];            // 0 none, 1 being created, 2 ready, 3 unavailable (fall back to the default pool)
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaMallocAsync(ptr, bytes, s);
+    int st = state[dev].load(std::memory_order_acquire);
+    if (st == 0) {
+        int expected = 0;
+        if (state[dev].compare_exchange_strong(expected, 1, std::memory_order_acq_rel)) {
+            cudaMemPoolProps props;
+            memset(&props, 0, sizeof(props));
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            cudaMemPool_t pool = nullptr;
+            bool ok = cudaMemPoolCreate(&pool, &props) == cudaSuccess;
+            if (ok) {
+                const char* env = getenv("CKFFT_B200_POOL_KEEP_MB");
+                const long long mb = env && *env ? atoll(env) : 2304;
+                unsigned long long keep = (unsigned long long) (mb < 0 ? 0 : mb) << 20;
+                ok = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess;
+            }
+            if (ok) pools[dev] = pool;
+            else cudaGetLastError();
+            state[dev].store(ok ? 2 : 3, std::memory_order_release);
+        }
+        while ((st = state[dev].load(std::memory_order_acquire)) == 1) { }
+    } else {
+        while (st == 1) st = state[dev].load(std::memory_order_acquire);
+    }
+    if (st != 2) return cudaMallocAsync(ptr, bytes, s);
+    return cudaMallocFromPoolAsync(ptr, bytes, pools[dev], s);
+}
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -765,7 +845,7 @@ int CkFftB200GetPlan(int n, int isReal, CkFftB200Plan* plan)
         if (n > (1 << 30)) return 0;
         int npass = 0, L[3];
         ckb::four_step_plan(ilog2i(m), &npass, L);
-        plan->passes = npass + (isReal ? 1 : 0);      // real: + one element-wise split / twist pass
+        plan->passes = npass + ((isReal && m > (1 << 20)) ? 1 : 0);   // real, three-pass lengths: + one element-wise split / twist pass (fused below that)
         for (int i = 0; i < npass && i < 2; ++i) {
             const ckb::PlanRow* r = ckb::find_plan(L[i]);
             plan->radix[i][0] = r->R0;

@@ -2,6 +2,7 @@
 #include "tile_launch.h"
 #include "pipe_kernel.cuh"
 #include "plans.h"
+#include <stdio.h>
 
 namespace ckb {
 
@@ -89,13 +90,14 @@ bool pipe_enabled()
     return env_ll("CKFFT_B200_PIPE", 1) != 0 && tensor_map_encoder() != nullptr;   // read per call: tests flip it
 }
 
-template <int L0, int L1, int MINB, bool INV, int NBUF, bool REAL = false>
+template <int L0, int L1, int MINB, bool INV, int NBUF, int MODE = PIPE_C2C>
 static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const cf* table, int log2_nt, const BigTwiddles& tw,
-                                   cudaStream_t s, long long out_stride = 0)
+                                   cudaStream_t s, long long out_stride = 0, long long in_stride = 0)
 {
     using A = typename PipeTile<L0, INV, KIND_COLUMN>::type;
     using B = typename PipeTile<L1, INV, KIND_LAST>::type;
-    using PC = PipeCfg<A, B, MINB, NBUF, REAL>;
+    using PC = PipeCfg<A, B, MINB, NBUF, MODE>;
+    constexpr bool REAL = MODE == PIPE_R2C, TWIST = MODE == PIPE_C2R;
     auto kern = pipe_kernel<PC, A, B>;
     constexpr int CTA = PC::THREADS + 64;                    // consumers + loader warp + signaller warp
     static int grid_cap[64] = {0};
@@ -120,8 +122,11 @@ static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const
     // tickets are in flight; a pass-2 item finds its dependencies met without waiting if it trails its pass-1 items by
     // at least W tickets (lag problems of S tickets), and a pass-1 item finds its ring slot drained if the ring is
     // another W tickets longer.  The ring is capped so that it stays resident in L2.
+    // Measured (tools/pipe_grid.py): with ping-pong buffers the loader runs a whole item ahead, so its dependencies must be
+    // met a whole item earlier: 1.4 x the window is the optimum at 2^15 / 2^16 (0.539 -> 0.554, 0.523 -> 0.550 of the copy
+    // peak); with one buffer the bare window is (deeper lags only push the ring out of L2).
     const long long window = ((long long) (2 + NBUF) * grid + S - 1) / S;
-    long long lag = env_ll("CKFFT_B200_PIPE_LAG", window + 1);
+    long long lag = env_ll("CKFFT_B200_PIPE_LAG", NBUF == 2 ? window * 7 / 5 : window + 1);
     long long slots = env_ll("CKFFT_B200_PIPE_RING", 2 * lag);
     const long long cap = (env_ll("CKFFT_B200_PIPE_RING_MB", 64) << 20) / (N * 8);
     if (slots > cap) slots = cap;
@@ -133,13 +138,14 @@ static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const
     const size_t ring_bytes = (size_t) slots * N * sizeof(cf);
     const size_t ctr_bytes = ((size_t) (2 * batch + 4) * sizeof(unsigned) + 127) & ~size_t(127);
     unsigned char* ws = nullptr;
-    if ((e = cudaMallocAsync((void**) &ws, ring_bytes + ctr_bytes, s)) != cudaSuccess) return e;
+    if ((e = scratch_alloc((void**) &ws, ring_bytes + ctr_bytes, s)) != cudaSuccess) return e;
     unsigned* ctr = (unsigned*) (ws + ring_bytes);
     if ((e = cudaMemsetAsync(ctr, 0, ctr_bytes, s)) != cudaSuccess) { cudaFreeAsync(ws, s); return e; }
 
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    if (!make_tile_map(&tmap, in, batch * L0, L1, A::BOX_ROWS, A::C)) { cudaFreeAsync(ws, s); return cudaErrorInvalidValue; }
+    // (the real inverse reads its input -- 8-byte aligned rows of M+1 values -- with plain loads: no tensor map)
+    if (!TWIST && !make_tile_map(&tmap, in, batch * L0, L1, A::BOX_ROWS, A::C)) { cudaFreeAsync(ws, s); return cudaErrorInvalidValue; }
 
     PipeParams p{};
     p.in = in; p.out = out; p.ring = (cf*) ws;
@@ -148,11 +154,36 @@ static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const
     p.batch = batch; p.ring_slots = (int) slots; p.lag = (int) lag;
     p.ticket = ctr; p.done1 = ctr + 4; p.done2 = ctr + 4 + batch;
     p.out_stride = out_stride ? out_stride : N + 1;
+    p.in_stride = in_stride ? in_stride : N + 1;
+    // Measured (B200, tools/gpu_check.py): one bulk copy per pass-2 tile instead of C: + 0.5 - 1 point everywhere; discarding the
+    // dead ring lines: 2^18 0.550 -> 0.560, 2^20 0.469 -> 0.492 (less write-back traffic at the power cap), but - 0.5 point
+    // at 2^15 / 2^16, where the ring is small enough to be overwritten in L2 before it is ever evicted.
+    p.flags = (int) env_ll("CKFFT_B200_PIPE_FLAGS", N >= (1 << 17) ? 3 : 1);
     p.tw_shift_real = tw.log2_tmax - ilog2(L0) - ilog2(L1) - 1;
-    if (REAL && p.tw_shift_real < 0) { cudaFreeAsync(ws, s); return cudaErrorInvalidValue; }
+    if ((REAL || TWIST) && p.tw_shift_real < 0) { cudaFreeAsync(ws, s); return cudaErrorInvalidValue; }
+#if CKB_PIPE_STATS
+    unsigned long long* dstats = nullptr;
+    cudaMalloc((void**) &dstats, 16 * sizeof(unsigned long long));
+    cudaMemsetAsync(dstats, 0, 16 * sizeof(unsigned long long), s);
+    p.stats = dstats;
+#endif
     kern<<<grid, CTA, PC::SMEM_BYTES, s>>>(p, tmap);
     count_launch();
     e = cudaGetLastError();
+#if CKB_PIPE_STATS
+    {
+        unsigned long long h[16];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h, dstats, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(dstats);
+        auto avg = [&](int sum, int cnt) { return h[cnt] ? (double) h[sum] / (double) h[cnt] : 0.0; };
+        fprintf(stderr, "pipe_stats L0=%d L1=%d mode=%d nbuf=%d grid=%d lag=%lld slots=%lld batch=%lld | per item (cycles): consumer wait %.0f; "
+                        "pass1: tile latency %.0f (%llu waits of %llu), compute %.0f; pass2: tile latency %.0f (%llu waits of %llu), compute %.0f | "
+                        "loader per item: ticket %.0f deps %.0f free-wait %.0f sig-wait %.0f\n",
+                L0, L1, MODE, NBUF, grid, lag, slots, batch, avg(0, 1), avg(2, 3), h[3], h[7], avg(6, 7), avg(4, 5), h[5], h[9], avg(8, 9),
+                avg(10, 14), avg(11, 14), avg(12, 14), avg(13, 14));
+    }
+#endif
     cudaError_t e2 = cudaFreeAsync(ws, s);
     return e != cudaSuccess ? e : e2;
 }
@@ -164,7 +195,7 @@ cudaError_t launch_pipe(bool inverse, int log2n, const cf* in, cf* out, long lon
     int npass, L[3];
     four_step_plan(log2n, &npass, L);
     if (npass != 2 || ((uintptr_t) in & 15)) return cudaErrorNotSupported;
-    const bool two = env_ll("CKFFT_B200_PIPE_NBUF", 1) == 2 && L[1] <= 256;     // ping-pong tile buffers (measurement knob)
+    const bool two = env_ll("CKFFT_B200_PIPE_NBUF", 2) == 2 && L[1] <= 256;     // ping-pong tile buffers where three CTAs still fit (CKFFT_B200_PIPE_NBUF=1: A/B)
 #define X(L0_, L1_, MINB_) \
     if (L[0] == L0_ && L[1] == L1_) { \
         if (two && L1_ <= 256) \
@@ -186,8 +217,31 @@ cudaError_t launch_pipe_r2c(int log2m, const cf* in, cf* out, long long batch, l
     int npass, L[3];
     four_step_plan(log2m, &npass, L);
     if (npass != 2 || ((uintptr_t) in & 15)) return cudaErrorNotSupported;
+    const bool two = env_ll("CKFFT_B200_PIPE_NBUF", 2) == 2 && L[1] <= 256;
 #define X(L0_, L1_, MINB_) \
-    if (L[0] == L0_ && L[1] == L1_) return launch_pipe_cfg<L0_, L1_, MINB_, false, 1, true>(in, out, batch, table, log2_nt, tw, s, out_stride);
+    if (L[0] == L0_ && L[1] == L1_) { \
+        if (two && L1_ <= 256) return launch_pipe_cfg<L0_, L1_, MINB_, false, (L1_ <= 256 ? 2 : 1), PIPE_R2C>(in, out, batch, table, log2_nt, tw, s, out_stride); \
+        return launch_pipe_cfg<L0_, L1_, MINB_, false, 1, PIPE_R2C>(in, out, batch, table, log2_nt, tw, s, out_stride); \
+    }
+    CKB_PIPE_PLANS(X)
+#undef X
+    return cudaErrorNotSupported;
+}
+
+// `batch` real inverse transforms of n = 2 * 2^log2m points: in = half spectra (rows of in_stride complex values, 8-byte
+// aligned), out = the real output viewed as 2^log2m complex values per frame (dense).  The twist is fused into pass 1.
+cudaError_t launch_pipe_c2r(int log2m, const cf* in, cf* out, long long batch, long long in_stride, const cf* table, int log2_nt,
+                            const BigTwiddles& tw, cudaStream_t s)
+{
+    int npass, L[3];
+    four_step_plan(log2m, &npass, L);
+    if (npass != 2) return cudaErrorNotSupported;
+    const bool two = env_ll("CKFFT_B200_PIPE_NBUF", 2) == 2 && L[1] <= 256;
+#define X(L0_, L1_, MINB_) \
+    if (L[0] == L0_ && L[1] == L1_) { \
+        if (two && L1_ <= 256) return launch_pipe_cfg<L0_, L1_, MINB_, true, (L1_ <= 256 ? 2 : 1), PIPE_C2R>(in, out, batch, table, log2_nt, tw, s, 0, in_stride); \
+        return launch_pipe_cfg<L0_, L1_, MINB_, true, 1, PIPE_C2R>(in, out, batch, table, log2_nt, tw, s, 0, in_stride); \
+    }
     CKB_PIPE_PLANS(X)
 #undef X
     return cudaErrorNotSupported;

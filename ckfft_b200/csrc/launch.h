@@ -31,6 +31,7 @@ cudaError_t launch_small_r2c(int M, const KernelParams& p, cudaStream_t s);     
 cudaError_t launch_small_c2r(int M, const KernelParams& p, cudaStream_t s);
 
 void count_launch();                  // api.cu: global launch counter
+cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t s);   // api.cu: stream-ordered scratch from the library's own pool (free with cudaFreeAsync)
 int sm_count_of_current_device();     // api.cu: cached multiProcessorCount
 
 // multi-pass path (four_step.cu)
@@ -42,6 +43,8 @@ bool pipe_enabled();                  // two-pass lengths as one L2-resident dat
 cudaError_t launch_pipe(bool inverse, int log2n, const cf* in, cf* out, long long batch, const cf* table, int log2_nt,
                         const BigTwiddles& tw, cudaStream_t s);
 cudaError_t launch_pipe_r2c(int log2m, const cf* in, cf* out, long long batch, long long out_stride, const cf* table, int log2_nt,
+                            const BigTwiddles& tw, cudaStream_t s);
+cudaError_t launch_pipe_c2r(int log2m, const cf* in, cf* out, long long batch, long long in_stride, const cf* table, int log2_nt,
                             const BigTwiddles& tw, cudaStream_t s);
 cudaError_t launch_real_split(const cf* z, cf* y, int n, long long batch, long long z_stride, long long y_stride,
                               const BigTwiddles& tw, cudaStream_t s);

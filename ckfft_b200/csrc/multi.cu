@@ -135,6 +135,8 @@ bool needs_pinning(const void* p)
 bool pin_enabled()
 {
     const char* e = getenv("CKFFT_B200_MULTI_PIN");
+    if (e && e[0] == '0') return false;
+    e = getenv("CKFFT_B200_PIN");                      // the single-device switch (api.cu) turns this one off, too
     return !(e && e[0] == '0');
 }
 

@@ -52,7 +52,27 @@ struct PipeParams {
     // real-forward kernels (PipeCfg::REAL): `in` is the real input viewed as M complex, `out` the half spectrum
     long long out_stride;   // complex elements per output row (M + 1 by default)
     int tw_shift_real;      // scales an exponent of W_(2M) to one of W_Tmax
+    // real-inverse kernels (PipeCfg::TWIST): `in` is the half spectrum, rows of in_stride complex (8-byte aligned
+    // only), `out` the real output viewed as M complex per frame
+    long long in_stride;
+    // development build only (-DCKB_PIPE_STATS=1, tools/pipe_stats.sh): cycle counters, see the bottom of launch_pipe_cfg
+    unsigned long long* stats;
+    // CKFFT_B200_PIPE_FLAGS (defaults chosen per length by measurement, four_step.cu): 1 = fetch a complex pass-2 tile (C
+    // adjacent ring rows = one contiguous block) with ONE bulk copy instead of C; 2 = discard the ring lines from L2 once the
+    // tile has landed (discard.global.L2: no write-back of dead data)
+    int flags;
 };
+
+#ifndef CKB_PIPE_STATS
+#define CKB_PIPE_STATS 0
+#endif
+#if CKB_PIPE_STATS
+#define CKB_STAT_ADD(i, v) (stat_acc[i] += (unsigned long long) (v))
+#define CKB_STAT_CLOCK() clock64()
+#else
+#define CKB_STAT_ADD(i, v) ((void) 0)
+#define CKB_STAT_CLOCK() 0LL
+#endif
 
 // gpu-scope poll that does not touch the L1 (no CCTL.IVALL behind it, unlike ld.acquire.gpu): the value comes from L2
 __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p)
@@ -120,13 +140,24 @@ __device__ __forceinline__ cf pipe_twiddle(const PipeParams& p, unsigned c, unsi
 }
 
 // A: column-pass plan (L0, C0 columns of the [L0][L1] problem per tile), B: last-pass plan (L1, C1 contiguous columns)
-template <class A, class B, int MINB_, int NBUF_ = 1, bool REAL_ = false>
+enum PipeMode { PIPE_C2C = 0, PIPE_R2C = 1, PIPE_C2R = 2 };
+
+template <class A, class B, int MINB_, int NBUF_ = 1, int MODE_ = PIPE_C2C>
 struct PipeCfg {
     // REAL: real forward transform of 2M points = this M-point complex transform + the split
     //   Y[k] = (Z[k] + conj Z[M-k]) - i W_2M^k (Z[k] - conj Z[M-k])        (src/ckfft/fft_real_default.cpp:13-63)
     // fused into pass 2: a tile holds C/2 columns c and their mirrors L0 - c (columns 0 and L0/2 mirror themselves),
     // so Z[k] and Z[M-k] meet in the tile and the half spectrum is the only thing written to HBM.
-    static constexpr bool REAL = REAL_;
+    static constexpr bool REAL = MODE_ == PIPE_R2C;
+    // TWIST: real inverse transform of 2M points = the twist
+    //   T[k] = (Y[k] + conj Y[M-k]) + i conj(W_2M^k) (Y[k] - conj Y[M-k])     (src/ckfft/fft_real_default.cpp:65-111)
+    // followed by this M-point inverse complex transform, fused into pass 1: the rows of the half spectrum hold M+1
+    // values and are only 8-byte aligned, which rules out TMA, so the consumers read Y[k] and Y[M-k] with plain 8-byte
+    // loads (both are 128-byte runs per half-warp; the second read of every element hits L2) and twist in registers
+    // on the way into stage 0 -- no twist pass over HBM, no intermediate array.
+    static constexpr bool TWIST = MODE_ == PIPE_C2R;
+    static_assert(MODE_ != PIPE_C2R || A::INV, "the real inverse runs the inverse complex transform");
+    static_assert(MODE_ != PIPE_R2C || !A::INV, "the real forward runs the forward complex transform");
     static constexpr int NBUF = NBUF_;            // tile buffers (each is staging area, then exchange buffer, of one item)
     static_assert(NBUF_ == 1 || NBUF_ == 2, "one buffer, or two in ping-pong");
     static_assert(A::THREADS == B::THREADS, "both passes run in the same CTA");
@@ -139,7 +170,7 @@ struct PipeCfg {
     static constexpr int XA = A::C * A::XBUF, XB = B::C * B::XBUF;
     static constexpr int XALL = ((XA > XB ? XA : XB) + 15) & ~15;   // whole 128-byte lines
     static constexpr int LUTA = A::LUT1, LUTB = B::LUT1;
-    static constexpr int SMEM_BYTES = 8 * (LUTA + LUTB + NBUF * XALL) + 128;
+    static constexpr int SMEM_BYTES = 8 * (LUTA + LUTB + NBUF * XALL) + 384;
     static_assert((XALL * 8) % 128 == 0, "tile buffer alignment");
     static_assert(((LUTA + LUTB) * 8) % 128 == 0, "tile buffer alignment");
 };
@@ -163,8 +194,16 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
     unsigned long long* bar_free = bar_full + 2;       // [2] every consumer has drained the buffer (stage-1 gather done)
     unsigned long long* bar_stored = bar_full + 4;     // [4] ring: every consumer has issued its global stores of item k (k & 3)
     unsigned long long* bar_sig = bar_full + 8;        // [4] ring: the signaller has handled item k (k & 3)
-    unsigned* item_slot = reinterpret_cast<unsigned*>(bar_full + 12);                        // [8]: ticket of item k at k & 7
+    // [8] item descriptors, item k at k & 7: {pass (0 = sentinel), problem, first column, ring slot}.  The loader decodes the
+    // ticket once; the 256 consumers and the signaller read one 16-byte word instead of each redoing the divisions.
+    uint4* item_desc = reinterpret_cast<uint4*>(bar_full + 12);
+    long long* req_clock = reinterpret_cast<long long*>(bar_full + 28);                     // [8] (statistics builds): when item k was requested
+    (void) req_clock;
     const int tid = threadIdx.x;
+#if CKB_PIPE_STATS
+    unsigned long long stat_acc[16] = {0};        // per thread (only consumer 0 and the loader use them), written out once at exit
+    auto stat_flush = [&] { for (int i = 0; i < 16; ++i) if (stat_acc[i]) atomicAdd(p.stats + i, stat_acc[i]); };
+#endif
 
     {
         const int shA = p.log2_nt - ilog2(L0), shB = p.log2_nt - ilog2(L1);
@@ -226,11 +265,9 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
         if (tid == THREADS + 32) {
             for (unsigned k = 0;; ++k) {                                   // signaller
                 mbar_wait_parked(bar_stored + (k & 3u), (k >> 2) & 1u);
-                const unsigned long long t = item_slot[k & 7u];
-                if (t >= total) return;                                    // sentinel (the consumers arrive for it, too)
-                int pass; long long prob; int c0;
-                decode(t, pass, prob, c0);
-                if (pass == 1) red_release_gpu_inc(p.done1 + prob);        // the consumers' stores are visible before the count
+                const uint4 d = item_desc[k & 7u];
+                if (d.x == 0u) return;                                     // sentinel (the consumers arrive for it, too)
+                if (d.x == 1u) red_release_gpu_inc(p.done1 + d.y);         // the consumers' stores are visible before the count
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_sig + (k & 3u))) : "memory");
             }
         }
@@ -256,37 +293,61 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
             }
         };
         auto request = [&](unsigned long long t, unsigned k) {        // item number k of this CTA carries ticket t
-            item_slot[k & 7u] = (unsigned) (t < total ? t : total);
             const unsigned b = k % NBUF;
             cf* stage = xall + b * PC::XALL;
             unsigned long long* full = bar_full + b;
             if (t >= total) {                                          // sentinel: complete the phase without a copy
+                item_desc[k & 7u] = make_uint4(0u, 0u, 0u, 0u);
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(full)) : "memory");
                 return;
             }
             int pass; long long prob; int c0;
             decode(t, pass, prob, c0);
+            item_desc[k & 7u] = make_uint4((unsigned) pass, (unsigned) prob, (unsigned) c0, (unsigned) (prob % p.ring_slots));
             if (pass == 1) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(full, L0 * A::C * 8);
+                if constexpr (PC::TWIST) {
+                    // nothing to stage: the consumers read the half spectrum themselves; the phase only hands them the item
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(full)) : "memory");
+                } else {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(full, L0 * A::C * 8);
 #pragma unroll
-                for (int r0 = 0; r0 < L0; r0 += A::BOX_ROWS)
-                    tensor_load_2d_hint(stage + r0 * A::C, &tmap_in, c0, (int) (prob * L0 + r0), full, pol_stream);
+                    for (int r0 = 0; r0 < L0; r0 += A::BOX_ROWS)
+                        tensor_load_2d_hint(stage + r0 * A::C, &tmap_in, c0, (int) (prob * L0 + r0), full, pol_stream);
+                }
             } else {
                 asm volatile("fence.proxy.async;" ::: "memory");       // other CTAs' generic stores -> our async-proxy reads
                 mbar_expect_tx(full, L1 * B::C * 8);
                 const cf* slot = p.ring + (prob % p.ring_slots) * N;
+                if (!PC::REAL && (p.flags & 1)) {
+                    bulk_load(stage, slot + (long long) c0 * L1, L1 * B::C * 8, full, pol_keep);      // C adjacent rows of the slot are contiguous
+                } else {
 #pragma unroll
-                for (int g = 0; g < B::C; ++g) bulk_load(stage + g * L1, slot + (long long) pass2_column(c0, g) * L1, L1 * 8, full, pol_keep);
+                    for (int g = 0; g < B::C; ++g) bulk_load(stage + g * L1, slot + (long long) pass2_column(c0, g) * L1, L1 * 8, full, pol_keep);
+                }
             }
         };
         for (unsigned j = 0;; ++j) {
+            const long long s0 = CKB_STAT_CLOCK();
             const unsigned long long t = atomicAdd(p.ticket, 1u);
+            const long long s1 = CKB_STAT_CLOCK();
             wait_deps(t);
+            const long long s2 = CKB_STAT_CLOCK();
             if (j >= (unsigned) NBUF) mbar_wait_parked(bar_free + j % NBUF, (j / NBUF - 1) & 1u);     // item j - NBUF has drained the buffer
+            const long long s3 = CKB_STAT_CLOCK();
             if (j >= 4u) mbar_wait_parked(bar_sig + (j & 3u), ((j >> 2) - 1) & 1u);                  // item j - 4 has been signalled
+            const long long s4 = CKB_STAT_CLOCK();
+#if CKB_PIPE_STATS
+            req_clock[j & 7u] = s4;
+            CKB_STAT_ADD(10, s1 - s0); CKB_STAT_ADD(11, s2 - s1); CKB_STAT_ADD(12, s3 - s2); CKB_STAT_ADD(13, s4 - s3); CKB_STAT_ADD(14, 1);
+#endif
             request(t, j);
-            if (t >= total) return;
+            if (t >= total) {
+#if CKB_PIPE_STATS
+                stat_flush();
+#endif
+                return;
+            }
         }
     }
 
@@ -296,27 +357,68 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
         const unsigned b = k % NBUF;
         cf* xb = xall + b * PC::XALL;                           // this item's buffer: staged tile first, exchange buffer after
         unsigned long long* bfree = bar_free + b;
+        const long long c0clk = CKB_STAT_CLOCK();
         mbar_wait_parked(bar_full + b, (k / NBUF) & 1u);
-        const unsigned long long cur = item_slot[k & 7u];
-        if (cur >= total) {                                     // sentinel: tell the signaller, then leave
+        const long long c1clk = CKB_STAT_CLOCK();
+        const uint4 desc = item_desc[k & 7u];
+        if (desc.x == 0u) {                                     // sentinel: tell the signaller, then leave
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_stored + (k & 3u))) : "memory");
+#if CKB_PIPE_STATS
+            if (tid == 0) stat_flush();
+#endif
             break;
         }
-        int pass; long long prob; int c0;
-        decode(cur, pass, prob, c0);
+        const int pass = (int) desc.x, c0 = (int) desc.z;
+        const long long prob = (long long) desc.y;
+#if CKB_PIPE_STATS
+        if (tid == 0) {
+            // [0] cycles the consumers waited for tiles, [1] items; per pass p: [2p] request -> landed (only when the consumer
+            // was already waiting, i.e. the true arrival time), [2p+1] count.  Loader: [10] ticket atomic, [11] dependency
+            // polls, [12] wait for a free buffer, [13] wait for the signaller, [14] items.
+            CKB_STAT_ADD(0, c1clk - c0clk); CKB_STAT_ADD(1, 1);
+            if (c1clk - c0clk > 300) { CKB_STAT_ADD(2 * pass, c1clk - req_clock[k & 7u]); CKB_STAT_ADD(2 * pass + 1, 1); }
+        }
+#endif
         if (pass == 1) {
             constexpr int L = A::L, E = A::E, T = A::T, C = A::C, R0 = A::R0, R1 = A::R1, LOGPAD = A::LOGPAD, XBUF = A::XBUF;
             const int g = tid % C, j = tid / C;               // along the columns, both stages
             cf v[E];
             constexpr int B0 = E / R0, STR0 = L / R0;
-            static_for<0, B0>([&](auto q_) {
-                constexpr int q = decltype(q_)::value;
-                static_for<0, R0>([&](auto t_) {
-                    constexpr int t = decltype(t_)::value;
-                    v[q * R0 + bitrev<R0>(t)] = xb[(j + q * T + t * STR0) * C + g];
+            if constexpr (PC::TWIST) {
+                // element (row, col) of the [L0][L1] view is T[i], i = row * L1 + col.  Pairwise definition of the twist pass
+                // (four_step.cuh real_twist_kernel, bit for bit): with k = min(i, M - i), y0 = Y[k], y1 = Y[M-k], c = f_k * dif,
+                //   T[k] = sum + c,   T[M-k] = conj(sum - c),   T[M/2] = 2 conj(Y[M/2]).
+                constexpr int M = (int) N;
+                const cf* __restrict__ yrow = p.in + prob * p.in_stride;
+                const int col = c0 + g;
+                static_for<0, B0>([&](auto q_) {
+                    constexpr int q = decltype(q_)::value;
+                    static_for<0, R0>([&](auto t_) {
+                        constexpr int t = decltype(t_)::value;
+                        const int i = (j + q * T + t * STR0) * L1 + col;
+                        const bool upper = 2 * i > M;
+                        const int k = upper ? M - i : i;
+                        const cf y0 = __ldg(yrow + k), y1 = __ldg(yrow + (M - k));
+                        const unsigned e = (unsigned) k << p.tw_shift_real;
+                        const cf w = cmul(__ldg(p.tw_lo + (e & ((1u << p.tw_h) - 1u))), __ldg(p.tw_hi + (e >> p.tw_h)));
+                        const cf sum = make_float2(y0.x + y1.x, y0.y - y1.y);
+                        const cf dif = make_float2(y0.x - y1.x, y0.y + y1.y);
+                        const cf cc = cmul(make_float2(w.y, w.x), dif);
+                        cf r = upper ? make_float2(sum.x - cc.x, -(sum.y - cc.y)) : make_float2(sum.x + cc.x, sum.y + cc.y);
+                        if (2 * i == M) r = make_float2(2.0f * y0.x, -2.0f * y0.y);
+                        v[q * R0 + bitrev<R0>(t)] = r;
+                    });
                 });
-            });
-            consumer_sync();                                  // the staged tile is consumed: the buffer now serves the exchange
+            } else {
+                static_for<0, B0>([&](auto q_) {
+                    constexpr int q = decltype(q_)::value;
+                    static_for<0, R0>([&](auto t_) {
+                        constexpr int t = decltype(t_)::value;
+                        v[q * R0 + bitrev<R0>(t)] = xb[(j + q * T + t * STR0) * C + g];
+                    });
+                });
+                consumer_sync();                              // the staged tile is consumed: the buffer now serves the exchange
+            }
             stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j);
             stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xb + g * XBUF, j, true);
             consumer_sync();
@@ -325,7 +427,7 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
             stage_math<T, E, R1, R0, INV, TW_LUT>(v, lutA, p.table, 0, j);
             constexpr int B1 = E / R1, STR1 = L / R1;
             const unsigned cc = (unsigned) (c0 + g);
-            cf* ocol = p.ring + (prob % p.ring_slots) * N + c0 + g;
+            cf* ocol = p.ring + (long long) desc.w * N + c0 + g;
             static_for<0, B1>([&](auto q_) {
                 constexpr int q = decltype(q_)::value;
                 const int jq = j + q * T;
@@ -348,6 +450,12 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
             const int g0 = tid / T, j0 = tid % T;             // stage 0 along the transform (contiguous columns)
             const int g1 = tid % C, j1 = tid / C;             // stage 1 along the columns (row-chunk stores)
             if (tid == 0) atomicAdd(p.done2 + prob, 1u);      // the copies have landed: the ring slot is no longer needed
+            if (!PC::REAL && (p.flags & 2)) {
+                // the tile's ring lines are dead now: drop them from L2 instead of letting them be written back to HBM
+                const char* dead = reinterpret_cast<const char*>(p.ring + (long long) desc.w * N + (long long) c0 * L1);
+                for (int ofs = tid * 128; ofs < L1 * C * 8; ofs += THREADS * 128)
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(dead + ofs) : "memory");
+            }
             cf v[E];
             constexpr int B0 = E / R0, STR0 = L / R0;
             static_for<0, B0>([&](auto q_) {
@@ -424,6 +532,9 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bfree)) : "memory");
             }
         }
+#if CKB_PIPE_STATS
+        if (tid == 0) { CKB_STAT_ADD(4 + 2 * pass, CKB_STAT_CLOCK() - c1clk); CKB_STAT_ADD(5 + 2 * pass, 1); }     // [6],[7] pass 1; [8],[9] pass 2: tile landed -> stores issued
+#endif
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_stored + (k & 3u))) : "memory");
     }
 }
