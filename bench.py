@@ -568,16 +568,17 @@ def measure_e2e(args, spec, ctx, rank, world, local_rank, dev, barrier, host_bar
     px[...] = nx[:sub]
     py[...] = 0
     dtp = timed(lambda: call(ctx, px, py), 2)
-    os.environ["CKFFT_B200_PIN"] = "0"
+    os.environ["CKFFT_B200_PIN"] = "1"
     try:
         dtu = timed(lambda: call(ctx, px, py), 2)
     finally:
         os.environ.pop("CKFFT_B200_PIN", None)
     pageable = {"value": round(spec["bytes"] * sub * world / dtp / 1e9, 2), "unit": "GB/s", "ms_per_step": round(dtp * 1e3, 3),
-                "sample": f"{sub} of {batch} transforms per GPU in numpy (malloc) arrays; the call page-locks them for its duration "
-                          "(cudaHostRegister + unregister inside the timed region) so that the copies overlap",
-                "without_registration": {"value": round(spec["bytes"] * sub * world / dtu / 1e9, 2), "ms_per_step": round(dtu * 1e3, 3),
-                                         "note": "CKFFT_B200_PIN=0: the driver stages pageable copies, H2D / D2H do not overlap"},
+                "sample": f"{sub} of {batch} transforms per GPU in numpy (malloc) arrays: the driver stages pageable copies, "
+                          "so H2D / D2H do not overlap",
+                "with_registration": {"value": round(spec["bytes"] * sub * world / dtu / 1e9, 2), "ms_per_step": round(dtu * 1e3, 3),
+                                      "note": "CKFFT_B200_PIN=1: the call page-locks the arrays for its duration (cudaHostRegister + "
+                                              "unregister inside the timed region)"},
                 "h2d_bytes_per_step": int(px.nbytes), "d2h_bytes_per_step": int(py.nbytes)}
     same = bool(np.array_equal(py.view(np.uint32), ny[:sub].view(np.uint32)))
     pageable["bit_identical_to_pinned_path"] = same

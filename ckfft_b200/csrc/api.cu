@@ -182,8 +182,10 @@ cudaError_t enqueue_large_real(const _CkFftContext* c, bool inverse, int n, cons
             const long long cnt = batch - done < chunk ? batch - done : chunk;
             e = ckb::launch_pipe_c2r(ilog2i(M), (const cf*) in + done * (M + 1), (cf*) ((float*) out + done * n), cnt, M + 1,
                                      c->dTable, c->log2Table, big_tw(c), s);
+            if (e == cudaErrorNotSupported && done == 0) break;      // no tensor map for this array: separate twist pass below
         }
-        return e;
+        if (e != cudaErrorNotSupported) return e;
+        cudaGetLastError();
     }
     const size_t per = (size_t) M * sizeof(cf);
     long long sub = (long long) (kScratchCapBytes / per);
@@ -399,9 +401,12 @@ int run_host_small(const _CkFftContext* c, Kind kind, int n, const void* in, voi
 }
 
 // Pageable host arrays: cudaMemcpyAsync on them is staged through the driver's bounce buffers and is synchronous, so
-// nothing overlaps (measured: 7 GB/s end to end against 75-95 GB/s for pinned arrays).  A call that moves at least
-// kPinThresholdBytes therefore page-locks the caller's arrays for its duration (cudaHostRegister) -- what a drop-in
-// caller's malloc'ed buffers need to reach the copy engines at full rate.  CKFFT_B200_PIN=0 disables it.
+// nothing overlaps (measured: 7 - 13 GB/s end to end against 75 - 95 GB/s for pinned arrays).  Page-locking the caller's
+// arrays for the duration of the call (cudaHostRegister) makes the copies asynchronous -- but registering and
+// unregistering costs about as much as the staged copy it saves: measured on the B200 box, 2 GiB in + 2 GiB out,
+// 12.7 GB/s with registration vs 12.9 without on one GPU, 15.2 vs 26.6 with two processes registering at once.  It is
+// therefore OPT-IN (CKFFT_B200_PIN=1, calls that move at least kPinThresholdBytes); a caller who reuses its buffers
+// should pin them once itself (CkFftB200HostAlloc or cudaHostRegister), which is what makes the host path fast.
 constexpr size_t kPinThresholdBytes = size_t(64) << 20;
 
 struct ScopedPin
@@ -428,7 +433,7 @@ int run_host(const _CkFftContext* c, Kind kind, int n, const void* in, void* out
 {
     const size_t ib = in_elems(kind, n) * in_elem_bytes(kind);     // bytes per transform
     const size_t ob = out_elems(kind, n) * out_elem_bytes(kind);
-    const bool pin = (ib + ob) * batch >= kPinThresholdBytes && getenv_flag("CKFFT_B200_PIN", 1);
+    const bool pin = (ib + ob) * batch >= kPinThresholdBytes && getenv_flag("CKFFT_B200_PIN", 0);
     ScopedPin pin_in(in, pin ? ib * batch : 0, true), pin_out(out, pin ? ob * batch : 0, false);
     static const size_t target = [] {                              // input bytes per chunk (default 32 MiB)
         const char* e = getenv("CKFFT_B200_CHUNK_MB");

@@ -142,10 +142,27 @@ static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const
     unsigned* ctr = (unsigned*) (ws + ring_bytes);
     if ((e = cudaMemsetAsync(ctr, 0, ctr_bytes, s)) != cudaSuccess) { cudaFreeAsync(ws, s); return e; }
 
-    CUtensorMap tmap;
+    CUtensorMap tmap, tmap2;
     memset(&tmap, 0, sizeof(tmap));
-    // (the real inverse reads its input -- 8-byte aligned rows of M+1 values -- with plain loads: no tensor map)
-    if (!TWIST && !make_tile_map(&tmap, in, batch * L0, L1, A::BOX_ROWS, A::C)) { cudaFreeAsync(ws, s); return cudaErrorInvalidValue; }
+    memset(&tmap2, 0, sizeof(tmap2));
+    int xshift[2] = { 0, 0 };
+    if (TWIST) {
+        // Half spectra: rows of in_stride (= M + 1 when dense) values, so the frames are not all 16-byte aligned.  Frames of
+        // parity q form a 3-D tensor [ceil((batch - q) / 2)][L0][L1 + shift] with frame stride 2 * in_stride elements (a multiple
+        // of 16 bytes whatever in_stride is) whose base is the 16-byte boundary at or below frame q; a frame that starts 8
+        // bytes above its boundary has its columns shifted by one.
+        const long long istr = in_stride ? in_stride : N + 1;
+        for (int q = 0; q < 2; ++q) {
+            const uintptr_t first = (uintptr_t) (in + q * istr);
+            xshift[q] = (int) ((first >> 3) & 1);
+            const long long frames = batch > q ? (batch - q + 1) / 2 : 1;
+            if (!make_tile_map3(q ? &tmap2 : &tmap, (const void*) (first & ~uintptr_t(15)), L1 + xshift[q], L0, frames, (long long) L1 * 8,
+                                2 * istr * 8, A::BOX_ROWS, PC::TWIST_W)) {
+                cudaFreeAsync(ws, s);
+                return cudaErrorNotSupported;              // the caller falls back to the separate twist pass
+            }
+        }
+    } else if (!make_tile_map(&tmap, in, batch * L0, L1, A::BOX_ROWS, A::C)) { cudaFreeAsync(ws, s); return cudaErrorInvalidValue; }
 
     PipeParams p{};
     p.in = in; p.out = out; p.ring = (cf*) ws;
@@ -159,6 +176,7 @@ static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const
     // dead ring lines: 2^18 0.550 -> 0.560, 2^20 0.469 -> 0.492 (less write-back traffic at the power cap), but - 0.5 point
     // at 2^15 / 2^16, where the ring is small enough to be overwritten in L2 before it is ever evicted.
     p.flags = (int) env_ll("CKFFT_B200_PIPE_FLAGS", N >= (1 << 17) ? 3 : 1);
+    p.twist_xshift[0] = xshift[0]; p.twist_xshift[1] = xshift[1];
     p.tw_shift_real = tw.log2_tmax - ilog2(L0) - ilog2(L1) - 1;
     if ((REAL || TWIST) && p.tw_shift_real < 0) { cudaFreeAsync(ws, s); return cudaErrorInvalidValue; }
 #if CKB_PIPE_STATS
@@ -167,7 +185,7 @@ static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const
     cudaMemsetAsync(dstats, 0, 16 * sizeof(unsigned long long), s);
     p.stats = dstats;
 #endif
-    kern<<<grid, CTA, PC::SMEM_BYTES, s>>>(p, tmap);
+    kern<<<grid, CTA, PC::SMEM_BYTES, s>>>(p, tmap, tmap2);
     count_launch();
     e = cudaGetLastError();
 #if CKB_PIPE_STATS
@@ -236,7 +254,7 @@ cudaError_t launch_pipe_c2r(int log2m, const cf* in, cf* out, long long batch, l
     int npass, L[3];
     four_step_plan(log2m, &npass, L);
     if (npass != 2) return cudaErrorNotSupported;
-    const bool two = env_ll("CKFFT_B200_PIPE_NBUF", 2) == 2 && L[1] <= 256;
+    const bool two = false;      // one (wider) tile buffer: two would not leave room for three CTAs per SM
 #define X(L0_, L1_, MINB_) \
     if (L[0] == L0_ && L[1] == L1_) { \
         if (two && L1_ <= 256) return launch_pipe_cfg<L0_, L1_, MINB_, true, (L1_ <= 256 ? 2 : 1), PIPE_C2R>(in, out, batch, table, log2_nt, tw, s, 0, in_stride); \

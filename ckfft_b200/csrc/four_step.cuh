@@ -243,17 +243,24 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
             const int jq = j1 + q * T;
             if constexpr (TC::KIND == KIND_COLUMN) {
                 // inter-pass twiddle W_TN^(cc * k), k = jq + u * STR1: geometric in u; with u = 4a + b it factors as
-                // A_a * B_b,  A_a = W^(cc * (jq + 4a*STR1)),  B_b = W^(cc * b*STR1): R1/4 + 3 table look-ups (two
-                // roundings deep) instead of R1.  Routed passes: k -> kk = prob*k_prob_mul + k*k_mul (linear, so the
-                // same factorisation holds with B_b = W^(cc * k_mul*b*STR1)).
+                // A_a * B_b,  B_b = s^b,  A_a = W^(cc * jq) * (s^4)^a,  s = W^(cc * STR1): two table look-ups and six
+                // multiplications per butterfly (the same arithmetic as the dataflow kernel, pipe_kernel.cuh, so that the two
+                // paths stay bit-identical).  Routed passes: k -> kk = prob*k_prob_mul + k*k_mul (linear, so the same
+                // factorisation holds with s = W^(cc * k_mul*STR1)).
                 const unsigned cc = (unsigned) (p.tw_col_base + ocol) >> p.tw_col_shift;
                 const unsigned kmul = TC::RT ? (unsigned) p.k_mul : 1u;
                 const unsigned koff = TC::RT ? (unsigned) (prob * p.k_prob_mul) : 0u;
-                cf bb[3];
-                static_for<1, 4>([&](auto b_) { constexpr int b = decltype(b_)::value; bb[b - 1] = big_twiddle(p, cc, kmul * (unsigned) (b * STR1), INV); });
+                cf bb[3], aav[R1 / 4];
+                {
+                    const cf s1 = big_twiddle(p, cc, kmul * (unsigned) STR1, INV);
+                    bb[0] = s1; bb[1] = cmul(s1, s1); bb[2] = cmul(bb[1], s1);
+                    const cf s4 = cmul(bb[1], bb[1]);
+                    aav[0] = big_twiddle(p, cc, koff + kmul * (unsigned) jq, INV);
+                    static_for<1, R1 / 4>([&](auto a_) { constexpr int a = decltype(a_)::value; aav[a] = cmul(aav[a - 1], s4); });
+                }
                 static_for<0, R1 / 4>([&](auto a_) {
                     constexpr int a = decltype(a_)::value;
-                    const cf aa = big_twiddle(p, cc, koff + kmul * (unsigned) (jq + 4 * a * STR1), INV);
+                    const cf aa = aav[a];
                     static_for<0, 4>([&](auto b_) {
                         constexpr int b = decltype(b_)::value;
                         constexpr int u = 4 * a + b;

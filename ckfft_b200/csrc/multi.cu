@@ -11,9 +11,10 @@
 //   CkFft*BatchMulti        shard -> post to the workers -> join; returns 1 only if every shard returned 1
 //   CkFftB200ShardRange     the shard arithmetic itself (pure host code; bench.py and the tests use the same function)
 //
-// Pageable host memory: cudaMemcpyAsync on it is staged by the driver and synchronous; a call that moves at least
-// kPinThreshold bytes therefore page-locks the caller's arrays for its duration (cudaHostRegister, portable across
-// the devices) unless CKFFT_B200_MULTI_PIN=0.  Arrays that are already pinned are left alone.
+// Pageable host memory: cudaMemcpyAsync on it is staged by the driver and synchronous.  With CKFFT_B200_PIN=1 a call that
+// moves at least kPinThreshold bytes page-locks the caller's arrays for its duration (cudaHostRegister, portable across
+// the devices); off by default because registration costs as much as it saves (api.cu, ScopedPin).  Arrays that are
+// already pinned are left alone.
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -134,10 +135,8 @@ bool needs_pinning(const void* p)
 
 bool pin_enabled()
 {
-    const char* e = getenv("CKFFT_B200_MULTI_PIN");
-    if (e && e[0] == '0') return false;
-    e = getenv("CKFFT_B200_PIN");                      // the single-device switch (api.cu) turns this one off, too
-    return !(e && e[0] == '0');
+    const char* e = getenv("CKFFT_B200_PIN");          // same opt-in switch as the single-device path (api.cu)
+    return e && e[0] == '1';
 }
 
 }  // namespace

@@ -55,6 +55,7 @@ struct PipeParams {
     // real-inverse kernels (PipeCfg::TWIST): `in` is the half spectrum, rows of in_stride complex (8-byte aligned
     // only), `out` the real output viewed as M complex per frame
     long long in_stride;
+    int twist_xshift[2];    // frames of parity q are described by tensor map q, whose columns are shifted by this (0 / 1)
     // development build only (-DCKB_PIPE_STATS=1, tools/pipe_stats.sh): cycle counters, see the bottom of launch_pipe_cfg
     unsigned long long* stats;
     // CKFFT_B200_PIPE_FLAGS (defaults chosen per length by measurement, four_step.cu): 1 = fetch a complex pass-2 tile (C
@@ -131,6 +132,13 @@ __device__ __forceinline__ void tensor_load_2d_hint(void* dst, const CUtensorMap
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 
+__device__ __forceinline__ void tensor_load_3d_hint(void* dst, const CUtensorMap* map, int x, int y, int z, unsigned long long* bar,
+                                                    unsigned long long policy)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
 __device__ __forceinline__ cf pipe_twiddle(const PipeParams& p, unsigned c, unsigned k, bool inverse)
 {
     const unsigned e = (c * k) << p.tw_shift;              // c*k < N <= 2^20
@@ -151,10 +159,19 @@ struct PipeCfg {
     static constexpr bool REAL = MODE_ == PIPE_R2C;
     // TWIST: real inverse transform of 2M points = the twist
     //   T[k] = (Y[k] + conj Y[M-k]) + i conj(W_2M^k) (Y[k] - conj Y[M-k])     (src/ckfft/fft_real_default.cpp:65-111)
-    // followed by this M-point inverse complex transform, fused into pass 1: the rows of the half spectrum hold M+1
-    // values and are only 8-byte aligned, which rules out TMA, so the consumers read Y[k] and Y[M-k] with plain 8-byte
-    // loads (both are 128-byte runs per half-warp; the second read of every element hits L2) and twist in registers
-    // on the way into stage 0 -- no twist pass over HBM, no intermediate array.
+    // followed by this M-point inverse complex transform, fused into pass 1.  Y[k] pairs with Y[M-k]: element (row r,
+    // column c) of the [L0][L1] view with (row L0-1-r, column L1-c).  A pass-1 tile therefore holds C/2 columns
+    // [ca, ca + C/2) and their C/2 mirror columns (slot g pairs with slot C-1-g), so that both members of every pair
+    // meet in the tile and every element is fetched from HBM exactly once.  The rows of the half spectrum hold M+1 values,
+    // i.e. every other frame starts 8 bytes off a 16-byte boundary; the tile is still fetched by TMA: frames of each
+    // parity get their own 3-D tensor map [frames/2][L0][L1 (+1)] whose base is the 16-byte boundary at or below the first
+    // such frame.  A TMA box must START on a 16-byte boundary as well (measured: an odd element coordinate raises "illegal
+    // instruction", tools/probes/tma3d_probe.cu) and the mirror columns of an aligned box begin 8 bytes off one, so every box
+    // is C/2 + 2 columns wide and the wanted columns sit at offset 0 or 1 inside it.  Columns 0
+    // and L1/2 pair with themselves: column 0 one row down (its r = 0 partner is Y[M], read with a plain load), column
+    // L1/2 takes the slot of the (non-existent) column L1 in the first tile and is read with plain loads.
+    // (First version: the consumers read Y[k] and Y[M-k] with plain 8-byte loads -- 19 000 cycles per pass-1 item instead
+    // of 7 000, no faster than the separate twist pass.)
     static constexpr bool TWIST = MODE_ == PIPE_C2R;
     static_assert(MODE_ != PIPE_C2R || A::INV, "the real inverse runs the inverse complex transform");
     static_assert(MODE_ != PIPE_R2C || !A::INV, "the real forward runs the forward complex transform");
@@ -168,7 +185,11 @@ struct PipeCfg {
     static constexpr int T1 = L1 / A::C;          // pass-1 tiles per problem
     static constexpr int T2 = L0 / B::C;          // pass-2 tiles per problem
     static constexpr int XA = A::C * A::XBUF, XB = B::C * B::XBUF;
-    static constexpr int XALL = ((XA > XB ? XA : XB) + 15) & ~15;   // whole 128-byte lines
+    // real inverse: the staged pass-1 tile is two halves of [L0][C/2 + 2] values (TMA boxes must start on 16-byte boundaries;
+    // the mirror columns of an aligned box start 8 bytes off one, so every box is fetched two columns wider)
+    static constexpr int TWIST_W = A::C / 2 + 2;
+    static constexpr int XT = MODE_ == PIPE_C2R ? 2 * A::L * TWIST_W : 0;
+    static constexpr int XALL = (((XA > XB ? XA : XB) > XT ? (XA > XB ? XA : XB) : XT) + 15) & ~15;   // whole 128-byte lines
     static constexpr int LUTA = A::LUT1, LUTB = B::LUT1;
     static constexpr int SMEM_BYTES = 8 * (LUTA + LUTB + NBUF * XALL) + 384;
     static_assert((XALL * 8) % 128 == 0, "tile buffer alignment");
@@ -176,7 +197,7 @@ struct PipeCfg {
 };
 
 template <class PC, class A, class B>
-__global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const PipeParams p, const __grid_constant__ CUtensorMap tmap_in)
+__global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const PipeParams p, const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in2)
 {
     constexpr int THREADS = PC::THREADS;          // consumer threads; two more warps serve them (loader, signaller)
     constexpr bool INV = A::INV;
@@ -306,8 +327,21 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
             item_desc[k & 7u] = make_uint4((unsigned) pass, (unsigned) prob, (unsigned) c0, (unsigned) (prob % p.ring_slots));
             if (pass == 1) {
                 if constexpr (PC::TWIST) {
-                    // nothing to stage: the consumers read the half spectrum themselves; the phase only hands them the item
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(full)) : "memory");
+                    // C/2 columns from ca and their C/2 mirror columns, as two [L0][C/2] halves of the buffer
+                    // Both boxes start at an even element coordinate.  Aligned frame (xs = 0): own columns from x = ca (offset 0
+                    // in the box), mirror columns L1-ca-H+1 .. from x = L1-ca-H (offset 1).  Frame 8 bytes above its boundary
+                    // (xs = 1, x = column + 1): own from x = ca (offset 1), mirror from x = L1-ca-H+2 (offset 0).
+                    constexpr int H = A::C / 2, W = PC::TWIST_W;
+                    const int q = (int) (prob & 1);
+                    const CUtensorMap* map = q ? &tmap_in2 : &tmap_in;
+                    const int xs = p.twist_xshift[q], ca = c0 / 2, z = (int) (prob >> 1);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(full, 2 * L0 * W * 8);
+#pragma unroll
+                    for (int r0 = 0; r0 < L0; r0 += A::BOX_ROWS) {
+                        tensor_load_3d_hint(stage + r0 * W, map, ca, r0, z, full, pol_stream);
+                        tensor_load_3d_hint(stage + (L0 + r0) * W, map, L1 - ca - H + 2 * xs, r0, z, full, pol_stream);
+                    }
                 } else {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mbar_expect_tx(full, L0 * A::C * 8);
@@ -384,31 +418,67 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
             const int g = tid % C, j = tid / C;               // along the columns, both stages
             cf v[E];
             constexpr int B0 = E / R0, STR0 = L / R0;
+            int jj = j;                                       // butterfly set this thread works on in stage 0
+            int ocolumn = c0 + g;                             // column of the [L0][L1] problem held by slot g
             if constexpr (PC::TWIST) {
-                // element (row, col) of the [L0][L1] view is T[i], i = row * L1 + col.  Pairwise definition of the twist pass
-                // (four_step.cuh real_twist_kernel, bit for bit): with k = min(i, M - i), y0 = Y[k], y1 = Y[M-k], c = f_k * dif,
+                // element (row r, column c) of the [L0][L1] view is T[i], i = r * L1 + c.  Pairwise definition of the twist pass
+                // (four_step.cuh real_twist_kernel; same operations, the factor W_2M^k one rounding apart -- see below): with
+                // k = min(i, M - i), y0 = Y[k], y1 = Y[M-k], c = f_k * dif,
                 //   T[k] = sum + c,   T[M-k] = conj(sum - c),   T[M/2] = 2 conj(Y[M/2]).
-                constexpr int M = (int) N;
+                // Slots [0, H) hold columns ca + g, slots H + m the mirror columns L1 - ca - (H-1) + m; slot g pairs with slot
+                // C-1-g, row r with row L0-1-r.  The threads of the mirror slots work on the mirrored butterfly set (T-1-j holds
+                // exactly the rows L0-1-r of j's rows), so the two halves of a warp request always read rows of opposite parity:
+                // conflict-free 64-byte rows.
+                constexpr int M = (int) N, H = C / 2, W = PC::TWIST_W;
                 const cf* __restrict__ yrow = p.in + prob * p.in_stride;
-                const int col = c0 + g;
+                const int ca = c0 / 2, half = g / H, pos = g % H;
+                const int xs = p.twist_xshift[prob & 1];             // where the wanted columns start inside the two boxes
+                const int o_own = half == 0 ? xs : 1 - xs, o_mir = half == 0 ? 1 - xs : xs;
+                const bool self_mid = c0 == 0 && g == C - 1;       // column L1/2 (pairs with itself): straight from global memory
+                const bool self_zero = c0 == 0 && g == 0;          // column 0 pairs with itself, one row down; its row 0 with Y[M]
+                ocolumn = self_mid ? L1 / 2 : (half == 0 ? ca + pos : L1 - ca - (H - 1) + pos);
+                jj = half == 0 ? j : T - 1 - j;
+                const cf* own_base = xb + half * (L * W) + pos + o_own;                   // [row][W]
+                const cf* mir_base = xb + (1 - half) * (L * W) + (H - 1 - pos) + o_mir;
+                static_assert(32 % R0 == 0, "the row step of a stage-0 butterfly is a multiple of 1/64 turn of W_2M");
                 static_for<0, B0>([&](auto q_) {
                     constexpr int q = decltype(q_)::value;
+                    // Twist factors.  The thread's R0 elements of this butterfly are L1 * STR0 = M / R0 apart, so
+                    //   W_2M^(i0 + t * M/R0) = W_2M^i0 * W_(2 R0)^t :
+                    // ONE two-level table look-up per butterfly (i0 = the t = 0 element) times compile-time constants instead
+                    // of a look-up per element (that was 10 % + 13 % of the kernel's stall samples, all waiting on table loads).
+                    // Elements of the upper half use k = M - i:  W_2M^(M-i) = -conj(W_2M^i), exact.
+                    const int i0 = (jj + q * T) * L1 + ocolumn;
+                    const unsigned e0 = (unsigned) i0 << p.tw_shift_real;
+                    const cf wbase = cmul(__ldg(p.tw_lo + (e0 & ((1u << p.tw_h) - 1u))), __ldg(p.tw_hi + (e0 >> p.tw_h)));
                     static_for<0, R0>([&](auto t_) {
                         constexpr int t = decltype(t_)::value;
-                        const int i = (j + q * T + t * STR0) * L1 + col;
+                        const int r = jj + q * T + t * STR0;
+                        cf own, mir;
+                        if (self_mid) {
+                            own = __ldg(yrow + r * L1 + L1 / 2);
+                            mir = __ldg(yrow + (L - 1 - r) * L1 + L1 / 2);
+                        } else if (self_zero) {
+                            own = own_base[r * W];
+                            mir = r == 0 ? __ldg(yrow + M) : own_base[(L - r) * W];
+                        } else {
+                            own = own_base[r * W];
+                            mir = mir_base[(L - 1 - r) * W];
+                        }
+                        const int i = r * L1 + ocolumn;
                         const bool upper = 2 * i > M;
-                        const int k = upper ? M - i : i;
-                        const cf y0 = __ldg(yrow + k), y1 = __ldg(yrow + (M - k));
-                        const unsigned e = (unsigned) k << p.tw_shift_real;
-                        const cf w = cmul(__ldg(p.tw_lo + (e & ((1u << p.tw_h) - 1u))), __ldg(p.tw_hi + (e >> p.tw_h)));
+                        const cf y0 = upper ? mir : own, y1 = upper ? own : mir;
+                        const cf wi = cmul_w64<t * (32 / R0)>(wbase);                       // W_2M^i
+                        const cf w = upper ? make_float2(-wi.x, wi.y) : wi;                  // W_2M^k, k = min(i, M - i)
                         const cf sum = make_float2(y0.x + y1.x, y0.y - y1.y);
                         const cf dif = make_float2(y0.x - y1.x, y0.y + y1.y);
                         const cf cc = cmul(make_float2(w.y, w.x), dif);
-                        cf r = upper ? make_float2(sum.x - cc.x, -(sum.y - cc.y)) : make_float2(sum.x + cc.x, sum.y + cc.y);
-                        if (2 * i == M) r = make_float2(2.0f * y0.x, -2.0f * y0.y);
-                        v[q * R0 + bitrev<R0>(t)] = r;
+                        cf res = upper ? make_float2(sum.x - cc.x, -(sum.y - cc.y)) : make_float2(sum.x + cc.x, sum.y + cc.y);
+                        if (2 * i == M) res = make_float2(2.0f * own.x, -2.0f * own.y);
+                        v[q * R0 + bitrev<R0>(t)] = res;
                     });
                 });
+                consumer_sync();                              // every pair has been read: the buffer now serves the exchange
             } else {
                 static_for<0, B0>([&](auto q_) {
                     constexpr int q = decltype(q_)::value;
@@ -419,27 +489,39 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
                 });
                 consumer_sync();                              // the staged tile is consumed: the buffer now serves the exchange
             }
-            stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j);
-            stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xb + g * XBUF, j, true);
+            stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, jj);
+            stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xb + g * XBUF, jj, true);
             consumer_sync();
             stage_gather<L, T, E, R1, LOGPAD, SRC_XBUF>(v, nullptr, xb + g * XBUF, j, true);
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bfree)) : "memory");
-            stage_math<T, E, R1, R0, INV, TW_LUT>(v, lutA, p.table, 0, j);
             constexpr int B1 = E / R1, STR1 = L / R1;
-            const unsigned cc = (unsigned) (c0 + g);
-            cf* ocol = p.ring + (long long) desc.w * N + c0 + g;
+            const unsigned cc = (unsigned) ocolumn;
+            cf tw_s[B1], tw_b[B1];                            // the two inter-pass twiddle look-ups of each butterfly (see below)
+            static_for<0, B1>([&](auto q_) {
+                constexpr int q = decltype(q_)::value;
+                tw_s[q] = pipe_twiddle(p, cc, (unsigned) STR1, INV);
+                tw_b[q] = pipe_twiddle(p, cc, (unsigned) (j + q * T), INV);
+            });
+            stage_math<T, E, R1, R0, INV, TW_LUT>(v, lutA, p.table, 0, j);
+            cf* ocol = p.ring + (long long) desc.w * N + ocolumn;
             static_for<0, B1>([&](auto q_) {
                 constexpr int q = decltype(q_)::value;
                 const int jq = j + q * T;
-                cf bb[3];
-                static_for<1, 4>([&](auto b_) { constexpr int b = decltype(b_)::value; bb[b - 1] = pipe_twiddle(p, cc, (unsigned) (b * STR1), INV); });
+                // inter-pass twiddle W_N^(cc * k), k = jq + u * STR1: geometric in u; with u = 4a + b it factors as A_a * B_b,
+                // B_b = s^b, A_a = W^(cc*jq) * (s^4)^a, s = W^(cc*STR1): TWO table look-ups per butterfly (tw_b[q], fetched before
+                // the butterfly arithmetic so that their latency hides behind it) and six multiplications.  (Round 1 looked up
+                // all R1/4 + 3 factors: 14 dependent L1 loads per thread at the end of the item; 2^16: 0.556 -> 0.618.)
+                cf bb[3], aa[R1 / 4];
+                bb[0] = tw_s[q]; bb[1] = cmul(tw_s[q], tw_s[q]); bb[2] = cmul(bb[1], tw_s[q]);
+                const cf s4 = cmul(bb[1], bb[1]);
+                aa[0] = tw_b[q];
+                static_for<1, R1 / 4>([&](auto a_) { constexpr int a = decltype(a_)::value; aa[a] = cmul(aa[a - 1], s4); });
                 static_for<0, R1 / 4>([&](auto a_) {
                     constexpr int a = decltype(a_)::value;
-                    const cf aa = pipe_twiddle(p, cc, (unsigned) (jq + 4 * a * STR1), INV);
                     static_for<0, 4>([&](auto b_) {
                         constexpr int b = decltype(b_)::value;
                         constexpr int u = 4 * a + b;
-                        cf val = cmul(v[q * R1 + u], aa);
+                        cf val = cmul(v[q * R1 + u], aa[a]);
                         if constexpr (b > 0) val = cmul(val, bb[b - 1]);
                         ocol[(long long) (jq + u * STR1) * L1] = val;          // stays in L2 (default policy)
                     });
@@ -507,8 +589,14 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
                 const int gm = (self0 || selfh) ? g1 : (g1 ^ H);              // partner slot
                 constexpr long long M = N;
                 cf* yrow = p.out + prob * p.out_stride;
+                static_assert(32 % R1 == 0, "the row step of a last-stage butterfly is a multiple of 1/64 turn of W_2M");
                 static_for<0, B1>([&](auto q_) {
                     constexpr int q = decltype(q_)::value;
+                    // split factors W_2M^k, k = col + L0 * (j1 + q*T + u*STR1): rows u are L0 * STR1 = M / R1 apart, so one table
+                    // look-up per butterfly (u = 0) times the constants W_(2 R1)^u serves all of them (as in the inverse's twist)
+                    const unsigned k0 = (unsigned) col + (unsigned) L0 * (unsigned) (j1 + q * T);
+                    const unsigned e0 = k0 << p.tw_shift_real;
+                    const cf wbase = cmul(__ldg(p.tw_lo + (e0 & ((1u << p.tw_h) - 1u))), __ldg(p.tw_hi + (e0 >> p.tw_h)));
                     static_for<0, R1 / 2>([&](auto u_) {
                         constexpr int u = decltype(u_)::value;
                         const int kr = j1 + q * T + u * STR1;                  // row < L/2: bin k = col + L0 * kr < M/2
@@ -516,8 +604,7 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
                         const cf z0 = v[q * R1 + u];
                         const cf z1 = (self0 && kr == 0) ? z0 : xb[gm * ZP + km];
                         const unsigned k = (unsigned) col + (unsigned) L0 * (unsigned) kr;
-                        const unsigned e = k << p.tw_shift_real;
-                        const cf w = cmul(__ldg(p.tw_lo + (e & ((1u << p.tw_h) - 1u))), __ldg(p.tw_hi + (e >> p.tw_h)));
+                        const cf w = cmul_w64<u * (32 / R1)>(wbase);
                         const cf sum = make_float2(z0.x + z1.x, z0.y - z1.y);
                         const cf dif = make_float2(z0.x - z1.x, z0.y + z1.y);
                         const cf cc = cmul(make_float2(-w.y, w.x), dif);

@@ -47,6 +47,20 @@ static bool make_tile_map(CUtensorMap* map, const cf* base, long long rows, int 
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 3-D view [nz][ny][nx] of 8-byte elements with byte strides {ystride, zstride} (multiples of 16), boxes of 1 x box_rows x box_cols
+static bool make_tile_map3(CUtensorMap* map, const void* base, long long nx, long long ny, long long nz, long long ystride_bytes,
+                           long long zstride_bytes, int box_rows, int box_cols)
+{
+    TensorMapEncodeTiledFn enc = tensor_map_encoder();
+    if (!enc || ((uintptr_t) base & 15) || (ystride_bytes & 15) || (zstride_bytes & 15) || nx <= 0 || ny <= 0 || nz <= 0) return false;
+    const cuuint64_t gdim[3] = { (cuuint64_t) nx, (cuuint64_t) ny, (cuuint64_t) nz };
+    const cuuint64_t gstride[2] = { (cuuint64_t) ystride_bytes, (cuuint64_t) zstride_bytes };
+    const cuuint32_t box[3] = { (cuuint32_t) box_cols, (cuuint32_t) box_rows, 1 };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void*) base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int tile_prefetch_mode()
 {
     static int mode = -1;

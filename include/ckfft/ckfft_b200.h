@@ -123,9 +123,10 @@ int CkFftB200ContextDevice(const CkFftContext* context);
  *       if a replica cannot be created; CkFftB200LastError() says why.
  *   CkFft{ComplexForward,ComplexInverse,RealForward,RealInverse}BatchMulti
  *       the CkFft*Batch call of the same name on HOST arrays (pageable or pinned; dense strides), same checks and
- *       1 / 0 return.  Calls that move >= 64 MiB page-lock pageable arrays for their duration (cudaHostRegister) so
- *       that the copies of all devices run asynchronously; CKFFT_B200_MULTI_PIN=0 disables that.  One call at a time
- *       per handle (concurrent callers are serialised).
+ *       1 / 0 return.  Pinned arrays (CkFftB200HostAlloc / cudaHostRegister) let the copies of all devices run
+ *       asynchronously; pageable arrays work but are staged by the driver (CKFFT_B200_PIN=1 page-locks them for the
+ *       duration of calls that move >= 64 MiB -- measured to cost as much as it saves).  One call at a time per handle
+ *       (concurrent callers are serialised).
  *   CkFftB200MultiContext(m, i)  the replica on device i (for device-resident data: use it with the *BatchAsync calls)
  *   CkFftB200ShardRange(batch, part, parts, &first, &count)
  *       the shard of `part`: [first, first + count); the first batch % parts shards are one transform longer.

@@ -108,9 +108,9 @@ def test_multi_error_returns():
 
 @pytest.mark.parametrize("pin", ["1", "0"])
 def test_multi_large_pageable_call(pin, monkeypatch):
-    """>= 64 MiB of pageable memory: the call page-locks the arrays for its duration (or not, CKFFT_B200_MULTI_PIN=0);
-    either way the result is the single-device result and the arrays are ordinary memory again afterwards"""
-    monkeypatch.setenv("CKFFT_B200_MULTI_PIN", pin)
+    """>= 64 MiB of pageable memory: with CKFFT_B200_PIN=1 the call page-locks the arrays for its duration, by default it
+    does not; either way the result is the single-device result and the arrays are ordinary memory again afterwards"""
+    monkeypatch.setenv("CKFFT_B200_PIN", pin)
     n, batch = 4096, 3000                                # 98 MB in + 98 MB out
     rng = np.random.default_rng(11)
     x = uniform_complex(rng, (batch, n))

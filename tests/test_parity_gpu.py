@@ -157,7 +157,7 @@ def test_pipelined_real_forward_fused_split(log2n, batch):
         finally:
             os.environ.pop("CKFFT_B200_PIPE_REAL", None)
         assert y.shape == (batch, n // 2 + 1)
-        assert rel_rms(y.cpu().numpy(), y0.cpu().numpy()) <= 1e-7
+        assert rel_rms(y.cpu().numpy(), y0.cpu().numpy()) <= 3e-7        # same operations; the split factors are one rounding apart
         orc = oracle.Restatement(n, 3)
         for b in (0, batch // 2, batch - 1):
             got = y[b].cpu().numpy()
@@ -171,7 +171,9 @@ def test_pipelined_real_forward_fused_split(log2n, batch):
 def test_pipelined_real_inverse_fused_twist(log2n, batch):
     """Real inverse transforms above the single-pass limit: the twist runs inside pass 1 of the dataflow kernel (the
     consumers read Y[k] and Y[M-k] with plain loads -- rows of n/2+1 values are only 8-byte aligned -- and twist in
-    registers).  Bit-identical to the separate twist pass + complex transform; checked against the oracle and fp64."""
+    registers; the tile is fetched by TMA although rows of n/2+1 values are only 8-byte aligned).  Agrees with the separate
+    twist pass + complex transform to rounding (its twist factors are one table value times a compile-time constant);
+    checked against the oracle."""
     import os
 
     n = 1 << log2n
@@ -193,15 +195,15 @@ def test_pipelined_real_inverse_fused_twist(log2n, batch):
         finally:
             os.environ.pop("CKFFT_B200_PIPE_REAL", None)
         assert x.shape == (batch, n)
-        assert torch.equal(x, x0), n
+        assert rel_rms(x.cpu().numpy(), x0.cpu().numpy()) <= 3e-7, n
         orc = oracle.Restatement(n, 3)
         for b in (0, batch // 2, batch - 1):
             got = x[b].cpu().numpy()
             assert rel_rms(got, orc.real_inverse(spec[b:b + 1], n)[0]) <= tolerance(n)
         orc.close()
-        # odd offsets: a batch that starts at an odd row of a larger array is 8-byte, not 16-byte, aligned
+        # odd offsets: a batch that starts at an odd row of a larger array has the frame alignments swapped
         y = ctx.real_inverse(sd[1:], n)
-        assert torch.equal(y, x0[1:])
+        assert torch.equal(y, x[1:])
 
 
 @pytest.mark.parametrize("log2n", [16, 17, 20, 22])
