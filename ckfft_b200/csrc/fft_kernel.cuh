@@ -448,7 +448,16 @@ struct Cfg {
     static constexpr bool RTWC = MODE_ == MODE_R2C ? (M_ == 64 || M_ == 128 || M_ == 8192)
                                : MODE_ == MODE_C2R ? (M_ == 32 || M_ == 64 || M_ == 128 || M_ == 4096 || M_ == 8192) : false;
     static constexpr int LOGPAD = ilog2(R0);
-    static constexpr int XBUF = M + (M >> LOGPAD) + 2;          // complex slots per group (+ slot M for the real modes)
+    // complex slots per group (+ slot M for the real modes).  Plans with several groups per half-warp (T = 4, 8) need a
+    // group pitch of 12 resp. 8 (mod 16) 8-byte words: with the raw pitch (6 or 10 mod 16) the groups of a half-warp land on
+    // each other's banks -- 4 to 8 conflicting lanes per exchange request (tools/bank_model.py, tests/test_bank_model.py).
+    static constexpr int XRAW = M + (M >> LOGPAD) + 2;
+    // Measured on B200 (fraction of the copy peak, raw -> conflict-free pitch): real n = 128 forward 0.79 -> 0.86, inverse
+    // 0.78 -> 0.88; real n = 256 inverse 0.75 -> 0.97 -- the split / twist passes go through the buffer, too.  The complex
+    // 128-point kernel measured 0.91 -> 0.85 with the wider pitch and keeps the raw one.
+    static constexpr bool WIDE_PITCH = MODE_ != MODE_C2C;
+    static constexpr int XBUF = !WIDE_PITCH ? XRAW
+                              : (M / E_) == 8 ? XRAW + (8 + 16 - XRAW % 16) % 16 : (M / E_) == 4 ? XRAW + (12 + 16 - XRAW % 16) % 16 : XRAW;
     static constexpr int LUT1 = TWR_ ? 0 : (R1 - 1) * R0;       // stage 1: Ns = R0
     static constexpr bool LUT2_SMEM = NSTAGE == 3 && (R2 - 1) * R0 * R1 <= 4096;
     static constexpr bool POW2 = NSTAGE == 3 && !LUT2_SMEM;        // last-stage twiddles from register power bases

@@ -233,11 +233,24 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
             __syncthreads();        // exchange consumed: the buffer is free for the next tile
             issue_tile(tile + gridDim.x);
         }
-        stage_math<T, E, R1, R0, INV, TW_LUT>(v, lut1, p.table, 0, j1);
-
-        // Results: this thread holds bins k = jq + u * (L / R1) of column c0 + g1, in natural u order.
+        // Results: this thread will hold bins k = jq + u * (L / R1) of column c0 + g1, in natural u order.
         constexpr int B1 = E / R1, STR1 = L / R1;
         const int ocol = c0 + g1;
+        // column pass: the two inter-pass twiddle look-ups of every butterfly (see below) are fetched BEFORE the butterfly
+        // arithmetic, so that the table loads' latency hides behind it
+        cf tw_s[B1], tw_b[B1];
+        if constexpr (TC::KIND == KIND_COLUMN) {
+            const unsigned cc = (unsigned) (p.tw_col_base + ocol) >> p.tw_col_shift;
+            const unsigned kmul = TC::RT ? (unsigned) p.k_mul : 1u;
+            const unsigned koff = TC::RT ? (unsigned) (prob * p.k_prob_mul) : 0u;
+            static_for<0, B1>([&](auto q_) {
+                constexpr int q = decltype(q_)::value;
+                tw_s[q] = big_twiddle(p, cc, kmul * (unsigned) STR1, INV);
+                tw_b[q] = big_twiddle(p, cc, koff + kmul * (unsigned) (j1 + q * T), INV);
+            });
+        }
+        stage_math<T, E, R1, R0, INV, TW_LUT>(v, lut1, p.table, 0, j1);
+
         static_for<0, B1>([&](auto q_) {
             constexpr int q = decltype(q_)::value;
             const int jq = j1 + q * T;
@@ -247,15 +260,12 @@ __global__ void __launch_bounds__(TC::THREADS, TC::MINB) tile_kernel(const TileP
                 // multiplications per butterfly (the same arithmetic as the dataflow kernel, pipe_kernel.cuh, so that the two
                 // paths stay bit-identical).  Routed passes: k -> kk = prob*k_prob_mul + k*k_mul (linear, so the same
                 // factorisation holds with s = W^(cc * k_mul*STR1)).
-                const unsigned cc = (unsigned) (p.tw_col_base + ocol) >> p.tw_col_shift;
-                const unsigned kmul = TC::RT ? (unsigned) p.k_mul : 1u;
-                const unsigned koff = TC::RT ? (unsigned) (prob * p.k_prob_mul) : 0u;
                 cf bb[3], aav[R1 / 4];
                 {
-                    const cf s1 = big_twiddle(p, cc, kmul * (unsigned) STR1, INV);
+                    const cf s1 = tw_s[q];
                     bb[0] = s1; bb[1] = cmul(s1, s1); bb[2] = cmul(bb[1], s1);
                     const cf s4 = cmul(bb[1], bb[1]);
-                    aav[0] = big_twiddle(p, cc, koff + kmul * (unsigned) jq, INV);
+                    aav[0] = tw_b[q];
                     static_for<1, R1 / 4>([&](auto a_) { constexpr int a = decltype(a_)::value; aav[a] = cmul(aav[a - 1], s4); });
                 }
                 static_for<0, R1 / 4>([&](auto a_) {

@@ -68,3 +68,24 @@ def test_small_kernel_row_pitches():
             else:
                 a = [(t >> 1) * pitch + 2 * (c // 2) + (t & 1) for t in range(32)]
             assert conflict_free(a), (M, c)
+
+
+def test_cooperative_plans_group_pitch_is_conflict_free():
+    """fft_kernel.cuh Cfg::XBUF: plans whose half-warps hold several groups (T = 4, 8) need a group pitch of 12 resp. 8 mod 16;
+    the raw pitch M + M/R0 + 2 collided on 4-8 lanes per request (tools/bank_model.py restates the index arithmetic)."""
+    import importlib.util
+    import io
+    import contextlib
+
+    spec = importlib.util.spec_from_file_location("bank_model", os.path.join(ROOT, "tools", "bank_model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    with contextlib.redirect_stdout(io.StringIO()):
+        spec.loader.exec_module(mod)
+    kernel_src = open(os.path.join(ROOT, "ckfft_b200", "csrc", "fft_kernel.cuh")).read()
+    assert "XRAW + (8 + 16 - XRAW % 16) % 16" in kernel_src and "XRAW + (12 + 16 - XRAW % 16) % 16" in kernel_src      # real-mode kernels
+    for (M, E, R0, R1, R2, G, MINB, TWR) in mod.plans:
+        T, raw = M // E, M + M // R0 + 2
+        X = raw + (8 + 16 - raw % 16) % 16 if T == 8 else raw + (12 + 16 - raw % 16) % 16 if T == 4 else raw
+        assert mod.model(M, E, R0, R1, G, X) == 0.0, (M, X)
+        assert X % 2 == 0                      # group buffers stay 16-byte aligned (bulk-copy destinations)
+    assert mod.model(64, 8, 8, 8, 16, 74) > 0  # the raw pitch did collide

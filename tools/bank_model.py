@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """Bank model of the single-pass cooperative kernels' exchange buffer (fft_kernel.cuh), per plan of plans.h: average number
 of conflicting lanes per 8-byte warp request for the current group pitch and the smallest conflict-free pitch.  No GPU needed.
-Finding (round 1, not yet applied -- needs a GPU run): plans with several groups per half-warp (M = 16 .. 128, T = 4 or 8)
-collide because the group pitch M + M/R0 + 2 is 6 or 10 mod 16; a pitch of 8 mod 16 (T = 8) / 12 mod 16 (T = 4) is free."""
+Finding (round 1): plans with several groups per half-warp (M = 16 .. 128, T = 4 or 8) collide when the group pitch is the
+raw M + M/R0 + 2 (6 or 10 mod 16); a pitch of 8 mod 16 (T = 8) / 12 mod 16 (T = 4) is free.  Applied in round 2 (Cfg::XBUF)."""
 import os, re
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src = open(os.path.join(ROOT, "ckfft_b200", "csrc", "plans.h")).read()
@@ -31,8 +31,9 @@ def model(M, E, R0, R1, G, GS):
     return tot / max(cnt, 1)
 
 
-print("M      T  pitch  conflicting lanes/request   smallest free pitch (mod 16)")
+print("M      T  pitch  conflicting lanes/request   smallest free pitch (mod 16)   [raw pitch: conflicts]")
 for (M, E, R0, R1, R2, G, MINB, TWR) in plans:
-    T, X = M // E, M + M // R0 + 2
+    T, raw = M // E, M + M // R0 + 2
+    X = raw + (8 + 16 - raw % 16) % 16 if T == 8 else raw + (12 + 16 - raw % 16) % 16 if T == 4 else raw      # Cfg::XBUF (fft_kernel.cuh)
     best = min(range(X, X + 17), key=lambda gs: (model(M, E, R0, R1, G, gs), gs))
-    print(f"{M:<6d} {T:<2d} {X:<6d} {model(M, E, R0, R1, G, X):<27.2f} {best} ({best % 16})")
+    print(f"{M:<6d} {T:<2d} {X:<6d} {model(M, E, R0, R1, G, X):<27.2f} {best} ({best % 16})   [{raw}: {model(M, E, R0, R1, G, raw):.2f}]")
