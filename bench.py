@@ -559,7 +559,7 @@ def measure_e2e(args, spec, ctx, rank, world, local_rank, dev, barrier, host_bar
     e2e = {"value": round(value, 2), "unit": "GB/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
            "ms_per_step": round(dt * 1e3, 3), "steps": args.e2e_steps,
            "gflops": round(spec["flops"] * batch * world / dt / 1e9, 1),
-           "path": "CkFft*Batch on pinned host arrays: 32 MiB chunks, 3 in flight, H2D/kernel/D2H overlapped; "
+           "path": "CkFft*Batch on pinned host arrays: 32 MiB chunks, up to 4 in flight, H2D / kernel / D2H on three role streams; "
                    "wall clock around the synchronous call, max over ranks"}
     # ---- pageable host arrays (what a drop-in caller's malloc gives): bounded sample of the same workload ----
     sub = min(batch, 1 << 18)
@@ -600,7 +600,7 @@ def measure_e2e(args, spec, ctx, rank, world, local_rank, dev, barrier, host_bar
                  "ms_per_step": round(dtm * 1e3, 3), "steps": args.e2e_steps, "transforms": batch,
                  "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                  "path": f"CkFft*BatchMulti from ONE process: {batch} transforms in pinned host arrays sharded over {ndev} GPU(s) "
-                         "(strong scaling of one batch), one host thread + 3-slot H2D/kernel/D2H pipeline per device"}
+                         "(strong scaling of one batch), one host thread + H2D / kernel / D2H pipeline per device"}
         mc.close()
     host_barrier()
     barrier()
@@ -653,6 +653,14 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # NUMA placement of the host arrays of the end-to-end leg: torchrun lets the ranks float over all cores, so first-touch
+    # puts a rank's pinned arrays on whatever node it happens to run on and the DMA of most GPUs crosses the socket link.
+    # Each rank therefore binds itself to the CPUs next to its GPU (sysfs local_cpulist) while it allocates them
+    # (CKFFT_BENCH_NUMA=0 disables it); the CPU baseline runs with the original affinity restored.
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import pcie_peak
+
+    numa = pcie_peak.bind_to_gpu_node(local_rank) if os.environ.get("CKFFT_BENCH_NUMA", "1") != "0" else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -767,6 +775,8 @@ def main():
                 secondary["dist30"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     host_barrier()
+    if numa is not None:
+        os.sched_setaffinity(0, numa[0])          # the CPU baseline gets every host core back
     if rank == 0:
         peak, peak_src = measured_peak()
         per_gpu = gbs / world
@@ -786,6 +796,8 @@ def main():
             "clocks": clocks,
         }
         if e2e is not None:
+            e2e["numa"] = (f"rank bound to the CPUs of its GPU's NUMA node ({numa[1]}) while allocating the pinned arrays"
+                           if numa is not None else "no NUMA binding (single node, or CKFFT_BENCH_NUMA=0)")
             line["e2e"] = e2e
             line["e2e_pageable"] = pageable
             line["e2e_multi"] = multi

@@ -266,16 +266,24 @@ bool check_call(const _CkFftContext* c, Kind kind, int n, const void* in, const 
     return true;
 }
 
-// per-thread staging for host-pointer calls: no mutable state lives in the (shared) context
+// per-thread staging for host-pointer calls: no mutable state lives in the (shared) context.
+// Three ROLE streams -- all H2D copies on one, all kernels on the second, all D2H copies on the third, chained by
+// events per buffer slot -- so that each DMA direction always has its next copy queued right behind the current one,
+// exactly like a plain back-to-back copy loop.  (Round 1 gave every slot its own stream carrying H2D -> kernel -> D2H:
+// a direction then idles whenever all slots happen to be in the other phases.  Fine on an idle link -- 92 of 98 GB/s on
+// one GPU -- but with the 8 GPUs of the box sharing the host it reached only 63 % of what plain copies achieve.)
 struct Staging
 {
     int device = -1;
-    static constexpr int kSlots = 3;
-    void* d_in[kSlots] = {nullptr, nullptr, nullptr};
-    void* d_out[kSlots] = {nullptr, nullptr, nullptr};
+    static constexpr int kSlots = 4;
+    void* d_in[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    void* d_out[kSlots] = {nullptr, nullptr, nullptr, nullptr};
     size_t in_cap = 0, out_cap = 0;
     int in_slots = 0, out_slots = 0;           // buffers currently allocated (a single-chunk call allocates one pair)
-    cudaStream_t stream[kSlots] = {nullptr, nullptr, nullptr};
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[kSlots] = {nullptr, nullptr, nullptr, nullptr};     // slot's H2D copy has landed
+    cudaEvent_t ev_k[kSlots] = {nullptr, nullptr, nullptr, nullptr};      // slot's kernel(s) have finished
+    cudaEvent_t ev_out[kSlots] = {nullptr, nullptr, nullptr, nullptr};    // slot's D2H copy has finished: the slot is free
 
     void release()
     {
@@ -286,22 +294,31 @@ struct Staging
         for (int i = 0; i < kSlots; ++i) {
             if (d_in[i]) cudaFree(d_in[i]);
             if (d_out[i]) cudaFree(d_out[i]);
-            if (stream[i]) cudaStreamDestroy(stream[i]);
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_k[i]) cudaEventDestroy(ev_k[i]);
+            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
             d_in[i] = d_out[i] = nullptr;
-            stream[i] = nullptr;
+            ev_in[i] = ev_k[i] = ev_out[i] = nullptr;
+        }
+        for (cudaStream_t* st : { &s_in, &s_k, &s_out }) {
+            if (*st) cudaStreamDestroy(*st);
+            *st = nullptr;
         }
         in_cap = out_cap = 0;
         in_slots = out_slots = 0;
         if (prev >= 0) cudaSetDevice(prev);
         device = -1;
     }
-    // `slots` = chunks that will be in flight (a call with one chunk needs one pair of buffers, not three)
+    // `slots` = chunks that will be in flight (a call with one chunk needs one pair of buffers, not four)
     cudaError_t reserve(int dev, size_t in_bytes, size_t out_bytes, int slots)
     {
         if (device != dev) { release(); device = dev; }
         cudaError_t e;
+        for (cudaStream_t* st : { &s_in, &s_k, &s_out })
+            if (!*st && (e = cudaStreamCreateWithFlags(st, cudaStreamNonBlocking)) != cudaSuccess) return e;
         for (int i = 0; i < kSlots; ++i)
-            if (!stream[i] && (e = cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+            for (cudaEvent_t* ev : { &ev_in[i], &ev_k[i], &ev_out[i] })
+                if (!*ev && (e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
         if ((e = grow(d_in, in_cap, in_slots, in_bytes, slots)) != cudaSuccess) return e;
         if ((e = grow(d_out, out_cap, out_slots, out_bytes, slots)) != cudaSuccess) return e;
         return cudaSuccess;
@@ -332,6 +349,15 @@ struct Staging
         in_cap = out_cap = 0;
         in_slots = out_slots = 0;
         cudaGetLastError();
+    }
+    cudaError_t drain()
+    {
+        cudaError_t e = cudaSuccess;
+        for (cudaStream_t st : { s_in, s_k, s_out }) {
+            const cudaError_t e1 = st ? cudaStreamSynchronize(st) : cudaSuccess;
+            if (e == cudaSuccess) e = e1;
+        }
+        return e;
     }
     // A worker thread that exits gives its staging buffers back.  (At process teardown the runtime may already be
     // gone; the calls then fail harmlessly and the driver reclaims the memory.)
@@ -477,9 +503,11 @@ struct ScopedPin
     ~ScopedPin() { if (p) { cudaHostUnregister(p); cudaGetLastError(); } }
 };
 
-// Host arrays: stream the batch through the GPU in chunks, three in flight
-// (H2D of chunk i+1, kernel of chunk i and D2H of chunk i-1 overlap on separate streams).
-int run_host(const _CkFftContext* c, Kind kind, int n, const void* in, void* out, size_t batch)
+// Host arrays: stream the batch through the GPU in chunks, up to four in flight
+// (H2D of chunk i+1, kernel of chunk i and D2H of chunk i-1 overlap on the three role streams of Staging).
+// `cursor` (multi-device scheduler, multi.cu): several threads -- one per device -- work on the SAME batch and draw chunk
+// numbers from the shared counter, so a device behind a slower host link simply takes fewer chunks.
+int run_host(const _CkFftContext* c, Kind kind, int n, const void* in, void* out, size_t batch, std::atomic<size_t>* cursor = nullptr)
 {
     const size_t ib = in_elems(kind, n) * in_elem_bytes(kind);     // bytes per transform
     const size_t ob = out_elems(kind, n) * out_elem_bytes(kind);
@@ -495,6 +523,11 @@ int run_host(const _CkFftContext* c, Kind kind, int n, const void* in, void* out
     if (per_chunk > batch) per_chunk = batch;
     // device buffers are padded to 16 bytes so that every slot keeps 8-byte aligned transforms
     Staging& st = tl_staging;
+    if (cursor) {
+        // shared batch: keep the chunk size every thread derives identical, and small enough that all devices get work
+        const size_t share = (batch + 63) / 64;
+        if (per_chunk > share) per_chunk = share ? share : 1;
+    }
     const size_t nchunks = (batch + per_chunk - 1) / per_chunk;
     const int slots = nchunks < (size_t) Staging::kSlots ? (int) nchunks : Staging::kSlots;
     cudaError_t e = st.reserve(c->device, per_chunk * ib + 16, per_chunk * ob + 16, slots);
@@ -507,26 +540,34 @@ int run_host(const _CkFftContext* c, Kind kind, int n, const void* in, void* out
     } give_back{ st, per_chunk * ib > kStagingKeepBytes || per_chunk * ob > kStagingKeepBytes };
 
     size_t done = 0;
-    int slot = 0;
-    while (done < batch) {
-        const size_t cnt = (batch - done < per_chunk) ? batch - done : per_chunk;
-        cudaStream_t s = st.stream[slot];
-        // the slot's previous chunk must have drained before its buffers are reused
-        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) { set_error("stream sync", e); return 0; }
-        if ((e = cudaMemcpyAsync(st.d_in[slot], (const char*) in + done * ib, cnt * ib, cudaMemcpyHostToDevice, s)) != cudaSuccess) {
-            set_error("H2D copy", e); return 0;
+    for (size_t chunk = 0; done < batch; ++chunk) {
+        if (cursor) {                                             // next unclaimed chunk of the shared batch
+            const size_t ci = cursor->fetch_add(1, std::memory_order_relaxed);
+            if (ci >= nchunks) break;
+            done = ci * per_chunk;
         }
-        e = enqueue(c, kind, n, st.d_in[slot], st.d_out[slot], (long long) cnt,
-                    (long long) in_elems(kind, n), (long long) out_elems(kind, n), s);
-        if (e != cudaSuccess) { set_error("kernel launch", e); return 0; }
-        if ((e = cudaMemcpyAsync((char*) out + done * ob, st.d_out[slot], cnt * ob, cudaMemcpyDeviceToHost, s)) != cudaSuccess) {
-            set_error("D2H copy", e); return 0;
+        const size_t cnt = (batch - done < per_chunk) ? batch - done : per_chunk;
+        const int slot = (int) (chunk % (size_t) slots);
+        // the slot's previous chunk must have left the device before its buffers are reused (host-side wait: the host
+        // runs at most `slots` chunks ahead of the D2H stream)
+        if (chunk >= (size_t) slots && (e = cudaEventSynchronize(st.ev_out[slot])) != cudaSuccess) { set_error("event sync", e); st.drain(); return 0; }
+        if ((e = cudaMemcpyAsync(st.d_in[slot], (const char*) in + done * ib, cnt * ib, cudaMemcpyHostToDevice, st.s_in)) != cudaSuccess ||
+            (e = cudaEventRecord(st.ev_in[slot], st.s_in)) != cudaSuccess) {
+            set_error("H2D copy", e); st.drain(); return 0;
+        }
+        if ((e = cudaStreamWaitEvent(st.s_k, st.ev_in[slot], 0)) == cudaSuccess)
+            e = enqueue(c, kind, n, st.d_in[slot], st.d_out[slot], (long long) cnt,
+                        (long long) in_elems(kind, n), (long long) out_elems(kind, n), st.s_k);
+        if (e == cudaSuccess) e = cudaEventRecord(st.ev_k[slot], st.s_k);
+        if (e != cudaSuccess) { set_error("kernel launch", e); st.drain(); return 0; }
+        if ((e = cudaStreamWaitEvent(st.s_out, st.ev_k[slot], 0)) != cudaSuccess ||
+            (e = cudaMemcpyAsync((char*) out + done * ob, st.d_out[slot], cnt * ob, cudaMemcpyDeviceToHost, st.s_out)) != cudaSuccess ||
+            (e = cudaEventRecord(st.ev_out[slot], st.s_out)) != cudaSuccess) {
+            set_error("D2H copy", e); st.drain(); return 0;
         }
         done += cnt;
-        slot = (slot + 1) % slots;
     }
-    for (int i = 0; i < Staging::kSlots; ++i)
-        if ((e = cudaStreamSynchronize(st.stream[i])) != cudaSuccess) { set_error("transform failed", e); return 0; }
+    if ((e = st.drain()) != cudaSuccess) { set_error("transform failed", e); return 0; }
     return 1;
 }
 
@@ -603,6 +644,16 @@ int run_async(CkFftContext* c, Kind kind, int n, const void* in, void* out, size
 
 namespace ckb {
 void set_last_error(const char* text) { set_error(text); }      // multi.cu reports through the same channel
+
+// multi.cu: one device's share of a batch in HOST arrays that several devices work on together (chunks are drawn from
+// `cursor`).  kind: 0 complex forward, 1 complex inverse, 2 real forward, 3 real inverse.  The caller has validated the call.
+int run_host_shared(CkFftContext* c, int kind, int n, const void* in, void* out, size_t batch, std::atomic<size_t>* cursor)
+{
+    if (!c || c->magic != kMagic) { set_error("invalid context"); return 0; }
+    DeviceGuard guard(c->device);
+    if (!guard.ok) { set_error("cannot select the context's device"); return 0; }
+    return run_host(c, (Kind) kind, n, in, out, batch, cursor);
+}
 
 // Stream-ordered scratch from the library's OWN memory pool (one per device).  The default pool of cudaMallocAsync
 // gives unused memory back to the driver at every synchronisation (release threshold 0), so a caller who synchronises

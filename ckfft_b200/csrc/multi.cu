@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <new>
@@ -32,7 +33,10 @@
 #include "ckfft/ckfft.h"
 #include "ckfft/ckfft_b200.h"
 
-namespace ckb { void set_last_error(const char* text); }   // api.cu
+namespace ckb {                                             // api.cu
+void set_last_error(const char* text);
+int run_host_shared(CkFftContext* c, int kind, int n, const void* in, void* out, size_t batch, std::atomic<size_t>* cursor);
+}
 
 namespace {
 
@@ -58,6 +62,7 @@ struct Job {
     const void* in = nullptr;
     void* out = nullptr;
     size_t batch = 0;
+    std::atomic<size_t>* cursor = nullptr;     // dynamic schedule: the whole batch + a shared chunk counter; static: this worker's shard
 };
 
 struct Worker {
@@ -102,7 +107,9 @@ void worker_main(Worker* w, int nMax, CkFftDirection dir)
             w->has_job = false;
         }
         int r = 1;
-        if (j.batch > 0) {
+        if (j.batch > 0 && j.cursor) {
+            r = ckb::run_host_shared(w->ctx, j.kind - JOB_C2C_FWD, j.n, j.in, j.out, j.batch, j.cursor);
+        } else if (j.batch > 0) {
             switch (j.kind) {
                 case JOB_C2C_FWD: r = CkFftComplexForwardBatch(w->ctx, j.n, (const CkFftComplex*) j.in, (CkFftComplex*) j.out, j.batch); break;
                 case JOB_C2C_INV: r = CkFftComplexInverseBatch(w->ctx, j.n, (const CkFftComplex*) j.in, (CkFftComplex*) j.out, j.batch); break;
@@ -285,7 +292,15 @@ static int run_multi(CkFftB200Multi* m, int kind, int n, const void* in, void* o
         if (needs_pinning(out)) pinned_out = cudaHostRegister(out, ob * batch, cudaHostRegisterPortable) == cudaSuccess;
         cudaGetLastError();          // a refused registration only means the copies stay synchronous
     }
+    // Schedule.  Dynamic (default for batches of at least 256 MiB): every device works on the whole batch and draws 32 MiB
+    // chunks from a shared counter, so the devices finish together even when their host links are not equally fast --
+    // on the 8-GPU box four of the GPUs get ~22 GB/s and one ~90 GB/s when all copy at once, and with equal static shards
+    // the call took as long as the slowest link needed (133 GB/s in total; plain concurrent copies: 212).  Static
+    // (CKFFT_B200_MULTI_STATIC=1, and small batches): contiguous shards as CkFftB200ShardRange cuts them.
     const int parts = (int) m->workers.size();
+    const char* st_env = getenv("CKFFT_B200_MULTI_STATIC");
+    const bool dynamic = parts > 1 && (ib + ob) * batch >= (size_t(256) << 20) && !(st_env && st_env[0] == '1');
+    std::atomic<size_t> cursor{0};
     for (int i = 0; i < parts; ++i) {
         Worker* w = m->workers[i];
         size_t first = 0, count = 0;
@@ -294,9 +309,10 @@ static int run_multi(CkFftB200Multi* m, int kind, int n, const void* in, void* o
             std::lock_guard<std::mutex> lk(w->m);
             w->job.kind = kind;
             w->job.n = n;
-            w->job.in = (const char*) in + first * ib;
-            w->job.out = (char*) out + first * ob;
-            w->job.batch = count;
+            w->job.in = dynamic ? in : (const void*) ((const char*) in + first * ib);
+            w->job.out = dynamic ? out : (void*) ((char*) out + first * ob);
+            w->job.batch = dynamic ? batch : count;
+            w->job.cursor = dynamic ? &cursor : nullptr;
             w->done = false;
             w->has_job = true;
         }

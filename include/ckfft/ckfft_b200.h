@@ -112,9 +112,12 @@ int CkFftB200ContextDevice(const CkFftContext* context);
  * Batched scheduler: one host call spreads a batch of independent transforms over several GPUs of the box.
  * The transforms of a batch share no state -- the reference says so itself ("the context does not contain state,
  * so contexts can be used simultaneously on different threads", inc/ckfft/ckfft.h:39-41) -- so the batch is cut into
- * contiguous shards (CkFftB200ShardRange), one per device; every device runs the ordinary host-buffer pipeline of the
- * CkFft*Batch calls (chunked H2D -> kernel -> D2H, three chunks in flight) on its own streams from its own host
- * thread, and the call returns when all shards are done.  There is no collective and no traffic between the GPUs.
+ * shards, every device runs the ordinary host-buffer pipeline of the CkFft*Batch calls (chunked H2D -> kernel -> D2H,
+ * several chunks in flight) on its own streams from its own host thread, and the call returns when all of them are
+ * done.  There is no collective and no traffic between the GPUs.  Small batches are cut into contiguous shards, one
+ * per device (CkFftB200ShardRange); batches of 256 MiB or more are scheduled dynamically -- every device draws 32 MiB
+ * chunks of the batch from a shared counter, so that devices behind a slower host link take fewer and all finish
+ * together (CKFFT_B200_MULTI_STATIC=1 forces static shards).  Results do not depend on the schedule.
  *
  *   CkFftB200MultiInit(nMax, direction, devices, nDevices)
  *       one context replica (CkFftInit(nMax, direction) on that device) and one worker thread per entry of

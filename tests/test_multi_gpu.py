@@ -124,6 +124,26 @@ def test_multi_large_pageable_call(pin, monkeypatch):
     assert x[0, 0] == 7.0
 
 
+@pytest.mark.parametrize("static", ["0", "1"])
+def test_multi_dynamic_schedule_matches_static(static, monkeypatch):
+    """Batches of >= 256 MiB are scheduled dynamically: every device draws 32 MiB chunks of the one batch from a shared
+    counter (a device behind a slower host link takes fewer).  Which device transforms which row cannot matter:
+    bit-identical to the single-device call, as with static shards (CKFFT_B200_MULTI_STATIC=1)."""
+    monkeypatch.setenv("CKFFT_B200_MULTI_STATIC", static)
+    n, batch = 4096, 5003                                # 164 MB in + 164 MB out, ragged last chunk
+    rng = np.random.default_rng(17)
+    x = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    devices = list(range(torch.cuda.device_count())) if torch.cuda.device_count() >= 2 else [0, 0, 0]
+    with ck.Context(n, ck.BOTH) as ctx, ck.MultiContext(n, ck.BOTH, devices) as mc:
+        want = ctx.real_forward(x)
+        got = mc.real_forward(x)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        back = mc.real_inverse(got, n)
+        assert np.array_equal(back.view(np.uint32), ctx.real_inverse(want, n).view(np.uint32))
+        xc = (x[:, ::2] + 1j * x[:, 1::2]).astype(np.complex64)     # 2048-point complex rows, 82 MB: static path inside the same handle
+        assert np.array_equal(mc.complex_forward(xc).view(np.uint32), ctx.complex_forward(xc).view(np.uint32))
+
+
 def test_multi_two_callers_share_one_handle():
     import threading
 

@@ -19,6 +19,53 @@ import threading
 import time
 
 
+def gpu_local_cpus(device: int):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None if the platform does not say."""
+    try:
+        import subprocess
+
+        # CUDA_VISIBLE_DEVICES is not set by torchrun, so the CUDA ordinal is nvidia-smi's index
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0]
+        bus = bus.lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                   # 00000000:1B:00.0 -> 0000:1b:00.0
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        return (sorted(cpus), node) if cpus else None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_node(device: int):
+    """Pin the calling thread to the CPUs next to `device`, so that the host memory it allocates next (first touch / cudaHostAlloc)
+    lands on that NUMA node.  Returns (previous affinity, node) or None if nothing was done."""
+    import os
+
+    info = gpu_local_cpus(device)
+    if not info:
+        return None
+    cpus, node = info
+    try:
+        prev = os.sched_getaffinity(0)
+        allowed = prev & set(cpus)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return prev, node
+    except (AttributeError, OSError):
+        return None
+
+
 def measure(device: int, total_bytes: int = 2 << 30, chunk_bytes: int = 32 << 20, pinned: bool = True, repeats: int = 3,
             host_src=None, host_dst=None):
     """-> dict(h2d, d2h, both_h2d, both_d2h, both) in GB/s (best of `repeats`).  `both` = bytes moved in the two
@@ -76,15 +123,19 @@ def main():
     ap.add_argument("--mb", type=int, default=2048)
     ap.add_argument("--chunk-mb", type=int, default=32)
     ap.add_argument("--pageable", action="store_true")
+    ap.add_argument("--numa", action="store_true", help="bind each worker to its GPU's NUMA node before it allocates host memory")
     args = ap.parse_args()
     n = min(args.gpus, torch.cuda.device_count())
-    out = {"gpus": n, "pinned": not args.pageable}
+    out = {"gpus": n, "pinned": not args.pageable, "numa_bound": bool(args.numa),
+           "gpu_numa_nodes": [(gpu_local_cpus(i) or (None, None))[1] for i in range(n)]}
     for concurrent in sorted({1, n}):
         results = [None] * concurrent
         gate = threading.Barrier(concurrent)
 
         def work(i):
             torch.cuda.set_device(i)
+            if args.numa:
+                bind_to_gpu_node(i)
             gate.wait()
             results[i] = measure(i, args.mb << 20, args.chunk_mb << 20, not args.pageable)
 
