@@ -127,7 +127,15 @@ cudaError_t enqueue_large_c2c(const _CkFftContext* c, bool inv, int n, const ckb
                               long long in_stride, long long out_stride, cudaStream_t s)
 {
     if (!c->dTwLo) return cudaErrorNotSupported;
-    if (in_stride != n || out_stride != n) return cudaErrorNotSupported;   // multi-pass path: dense batches only
+    if (in_stride != n || out_stride != n) {
+        // Padded rows.  The multi-pass kernels describe a batch as ONE dense [batch * L0][L1] array (tensor
+        // maps, ring slots), and a transform of >= 2^15 points fills the machine on its own: strided batches run one
+        // transform per launch sequence, each dense in itself.
+        cudaError_t e = cudaSuccess;
+        for (long long i = 0; i < batch && e == cudaSuccess; ++i)
+            e = enqueue_large_c2c(c, inv, n, in + i * in_stride, out + i * out_stride, 1, n, n, s);
+        return e;
+    }
     if (n <= (1 << 20) && ckb::pipe_enabled() && (((uintptr_t) in) & 15) == 0) {
         // two passes as one persistent kernel, intermediate ring resident in L2 (pipe_kernel.cuh)
         const long long chunk = 1LL << 20;                 // problems per launch (keeps the ticket in 32 bits)
@@ -161,8 +169,16 @@ cudaError_t enqueue_large_real(const _CkFftContext* c, bool inverse, int n, cons
     using ckb::cf;
     if (!c->dTwLo) return cudaErrorNotSupported;
     const int M = n / 2;
-    if ((!inverse && (in_stride != n || out_stride != M + 1)) || (inverse && (in_stride != M + 1 || out_stride != n)))
-        return cudaErrorNotSupported;
+    if ((!inverse && (in_stride != n || out_stride != M + 1)) || (inverse && (in_stride != M + 1 || out_stride != n))) {
+        // padded rows: one frame per launch sequence (see enqueue_large_c2c); strides are in elements of each array
+        cudaError_t e = cudaSuccess;
+        for (long long i = 0; i < batch && e == cudaSuccess; ++i) {
+            const void* fi = inverse ? (const void*) ((const cf*) in + i * in_stride) : (const void*) ((const float*) in + i * in_stride);
+            void* fo = inverse ? (void*) ((float*) out + i * out_stride) : (void*) ((cf*) out + i * out_stride);
+            e = enqueue_large_real(c, inverse, n, fi, fo, 1, inverse ? M + 1 : n, inverse ? n : M + 1, s);
+        }
+        return e;
+    }
     if (!inverse && M <= (1 << 20) && ckb::pipe_enabled() && getenv_flag("CKFFT_B200_PIPE_REAL", 1) && (((uintptr_t) in) & 15) == 0) {
         // real forward: half-length complex transform + split in ONE dataflow kernel (pipe_kernel.cuh, PipeCfg::REAL)
         const long long chunk = 1LL << 20;

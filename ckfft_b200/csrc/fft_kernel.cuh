@@ -52,6 +52,11 @@ struct KernelParams {
 };
 
 template <int LOGPAD> __device__ __forceinline__ int padidx(int p) { return p + (p >> LOGPAD); }
+// padidx(a + c) == padidx(a) + padoff(c) whenever c is a multiple of the padding period 2^LOGPAD.  The stage functions
+// use this to address a butterfly's R values as ONE run-time base plus compile-time offsets: ptxas does not find the
+// identity by itself and computed every padded index separately (4 integer instructions and one live register per
+// shared-memory access: 14-22 % of the instructions of the three-stage kernels, and the cause of their spills).
+template <int LOGPAD> __host__ __device__ constexpr int padoff(int c) { return c + (c >> LOGPAD); }
 
 __device__ __forceinline__ cf ld_stream(const cf* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(cf* p, cf v) { __stcs(p, v); }
@@ -61,6 +66,19 @@ __device__ __forceinline__ cf table_w(const cf* table, int idx, bool inverse)
     cf w = __ldg(table + idx);
     if (inverse) w.y = -w.y;
     return w;
+}
+
+// Table element base[c * 2^sh] for a compile-time c: the byte step 8 << sh goes through an opaque register so that the
+// address is ONE multiply-add (IMAD.WIDE.U32 base + c * step) instead of a run-time shift plus a 64-bit add per look-up.
+__device__ __forceinline__ unsigned table_step_bytes(int sh)
+{
+    unsigned r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(8u), "r"((unsigned) sh));
+    return r;
+}
+__device__ __forceinline__ cf table_at(const cf* __restrict__ base, unsigned c, unsigned step_bytes)
+{
+    return __ldg(reinterpret_cast<const cf*>(reinterpret_cast<const char*>(base) + (unsigned long long) step_bytes * c));
 }
 
 template <int T>
@@ -169,10 +187,20 @@ __device__ __forceinline__ void stage_gather(cf (&v)[E], const cf* __restrict__ 
 {
     constexpr int B = E / R;      // butterflies per thread
     constexpr int STR = M / R;    // distance between the R inputs of one butterfly
+    constexpr int PADW = 1 << LOGPAD;
     static_assert(B * R == E, "radix must divide the per-thread element count");
     static_for<0, B>([&](auto q_) {
         constexpr int q = decltype(q_)::value;
         const int jq = bfly_index<T, STR, PAIRED>(j, q);
+        // padded position of the butterfly's first input; the others are compile-time offsets from it (see padoff)
+        const cf* xq = xb;
+        (void) xq;
+        if constexpr (SRC == SRC_XBUF && STR % PADW == 0) {
+            if constexpr (T % PADW != 0)  xq = xb + padidx<LOGPAD>(jq);
+            else if constexpr (!PAIRED || (q & 1) == 0) xq = xb + padidx<LOGPAD>(j) + padoff<LOGPAD>((PAIRED ? q >> 1 : q) * T);
+            else if constexpr (q == 1)    xq = xb + padidx<LOGPAD>(jq);                  // STR - j, or STR/2 for thread 0
+            else                          xq = xb + padidx<LOGPAD>(STR - j) - padoff<LOGPAD>((q >> 1) * T);   // STR - (j + s*T), s >= 1
+        }
         static_for<0, R>([&](auto t_) {
             constexpr int t = decltype(t_)::value;
             constexpr int slot = q * R + bitrev<R>(t);
@@ -182,6 +210,8 @@ __device__ __forceinline__ void stage_gather(cf (&v)[E], const cf* __restrict__ 
                 if (valid) v[slot] = __ldg(gsrc + jq + t * STR);
             } else if constexpr (SRC == SRC_INBUF) {
                 v[slot] = xb[jq + t * STR];            // dense staging buffer filled by a bulk copy
+            } else if constexpr (STR % PADW == 0) {
+                v[slot] = xq[padoff<LOGPAD>(t * STR)];
             } else {
                 v[slot] = xb[padidx<LOGPAD>(jq + t * STR)];
             }
@@ -266,17 +296,38 @@ __device__ __forceinline__ void stage_scatter(const cf (&v)[E], cf* __restrict__
 {
     constexpr int B = E / R;
     constexpr int STR = M / R;
+    constexpr int PADW = 1 << LOGPAD;
     static_assert(DST != DST_GLOBAL || NS * R == M, "only the last stage writes global memory");
     static_for<0, B>([&](auto q_) {
         constexpr int q = decltype(q_)::value;
         const int jq = j + q * T;
+        (void) jq;
+        // one run-time base per butterfly, compile-time offsets for its R outputs (see padoff)
+        constexpr bool LIN_XCHG = DST == DST_XCHG && ((NS == 1 && R == PADW) || (NS > 1 && NS % PADW == 0));
+        constexpr bool LIN_XNAT = DST == DST_XNAT && STR % PADW == 0;
+        cf* xq = xb;
+        if constexpr (LIN_XCHG && NS == 1) {
+            xq = xb + j * (R + 1) + q * T * (R + 1);                   // padidx(jq * R + u) = jq * (R + 1) + u for u < R = 2^LOGPAD
+        } else if constexpr (LIN_XCHG) {
+            if constexpr (T % NS == 0) xq = xb + padidx<LOGPAD>((j / NS) * (NS * R) + (j & (NS - 1))) + padoff<LOGPAD>(q * T * R);
+            else                       xq = xb + padidx<LOGPAD>((jq / NS) * (NS * R) + (jq & (NS - 1)));
+        } else if constexpr (LIN_XNAT) {
+            if constexpr (T % PADW == 0) xq = xb + padidx<LOGPAD>(j) + padoff<LOGPAD>(q * T);
+            else                         xq = xb + padidx<LOGPAD>(jq);
+        }
         static_for<0, R>([&](auto u_) {
             constexpr int u = decltype(u_)::value;
             constexpr int slot = q * R + u;
             if constexpr (DST == DST_GLOBAL) {
                 if (valid) st_stream(gdst + jq + u * STR, v[slot]);
+            } else if constexpr (LIN_XNAT) {
+                xq[padoff<LOGPAD>(u * STR)] = v[slot];
             } else if constexpr (DST == DST_XNAT) {
                 xb[padidx<LOGPAD>(jq + u * STR)] = v[slot];
+            } else if constexpr (LIN_XCHG && NS == 1) {
+                xq[u] = v[slot];
+            } else if constexpr (LIN_XCHG) {
+                xq[padoff<LOGPAD>(u * NS)] = v[slot];
             } else {
                 const int p = (jq / NS) * (NS * R) + (jq & (NS - 1)) + u * NS;
                 xb[padidx<LOGPAD>(p)] = v[slot];
@@ -324,6 +375,16 @@ __device__ __forceinline__ void put_bin(cf* __restrict__ dst, int k, cf y)
     else                 st_stream(dst + k, y);
 }
 
+// the same through a pointer to the bin itself (float for the power spectrum, complex otherwise)
+template <bool AUDIO> struct BinType { typedef cf type; };
+template <> struct BinType<true> { typedef float type; };
+template <bool AUDIO>
+__device__ __forceinline__ void put_at(typename BinType<AUDIO>::type* __restrict__ p, cf y)
+{
+    if constexpr (AUDIO) __stcs(p, fmaf(y.x, y.x, y.y * y.y));
+    else                 st_stream(p, y);
+}
+
 // Real-forward split on a thread's mirror-paired butterflies (see bfly_index).  v holds, per pair slot s,
 // Z[p + u*STR] in block 2s and Z[pbar + u*STR] in block 2s+1 (natural u order).  Writes Y[0 .. M].
 //   Y[k] = (Z[k] + conj Z[M-k]) - i W_2M^k (Z[k] - conj Z[M-k]);  with c = i W^k * diff:
@@ -332,29 +393,37 @@ __device__ __forceinline__ void put_bin(cf* __restrict__ dst, int k, cf y)
 // exact table value loaded once per kernel) times the compile-time constant W_64^(s*32/E + u*32/R) -- no table traffic
 // per transform, one extra rounding like the register stage twiddles.  Which one is faster depends on the registers the
 // plan has left (Cfg::RTWC, by measurement).
+// Addresses: bin k = j + c lives at (row + j) + c and its mirror at (row + M - j) - c with c a compile-time constant, so
+// the 2 E stores and E/2 table loads of a thread hang off three pointers computed once per row (ptxas rebuilt every
+// 64-bit address from k: ~ 4 integer instructions per access).
 template <int M, int T, int E, int R, bool AUDIO, bool CONST_TW>
 __device__ __forceinline__ void r2c_paired_epilogue(const cf (&v)[E], cf* __restrict__ dst, const cf* __restrict__ table, int sh_real,
                                                     cf wj, int j, bool valid)
 {
     constexpr int B = E / R, STR = M / R;
+    typedef typename BinType<AUDIO>::type bin_t;
     static_assert(B % 2 == 0, "butterflies come in mirror pairs");
     static_assert(!CONST_TW || (32 % E == 0 && 16 % R == 0), "split factors are multiples of 1/64 turn");
-    auto emit = [&](cf z0, cf z1, int k, cf w) {                // w = W_2M^k; f = i w = (-w.y, w.x)
+    bin_t* __restrict__ lo = reinterpret_cast<bin_t*>(dst) + j;            // bin j + c      at lo[c]
+    bin_t* __restrict__ hi = reinterpret_cast<bin_t*>(dst) + (M - j);      // bin M - j - c  at hi[-c]
+    const cf* __restrict__ tj = table + ((long long) j << sh_real);        // W_2M^(j + c)   at tj[c << sh_real]
+    const unsigned tstep = table_step_bytes(sh_real);
+    (void) tj; (void) tstep;
+    auto emit = [&](cf z0, cf z1, int c, cf w) {                // c = k - j; w = W_2M^k; f = i w = (-w.y, w.x)
         const cf sum = make_float2(z0.x + z1.x, z0.y - z1.y);
         const cf dif = make_float2(z0.x - z1.x, z0.y + z1.y);
-        const cf c = cmul(make_float2(-w.y, w.x), dif);
-        put_bin<AUDIO>(dst, k, make_float2(sum.x - c.x, sum.y - c.y));
-        put_bin<AUDIO>(dst, M - k, make_float2(sum.x + c.x, -(sum.y + c.y)));
+        const cf cc = cmul(make_float2(-w.y, w.x), dif);
+        put_at<AUDIO>(lo + c, make_float2(sum.x - cc.x, sum.y - cc.y));
+        put_at<AUDIO>(hi - c, make_float2(sum.x + cc.x, -(sum.y + cc.y)));
     };
-    auto factor = [&](auto k64_, int k) -> cf {
+    auto factor = [&](auto k64_, int c) -> cf {
         if constexpr (CONST_TW) return cmul_w64<decltype(k64_)::value>(wj);
-        else                    return __ldg(table + (k << sh_real));
+        else                    return table_at(tj, (unsigned) c, tstep);
     };
     if (!valid) return;
     static_for<0, B / 2>([&](auto s_) {
         constexpr int s = decltype(s_)::value;
         constexpr int A = 2 * s * R, Bk = (2 * s + 1) * R;
-        const int p = j + s * T;
         if constexpr (s == 0) {
             // Thread 0's first pair holds butterflies 0 (block A) and STR/2 (block B), which mirror into
             // themselves: same arithmetic, different operands -- chosen with selects, no divergent branch.
@@ -363,30 +432,30 @@ __device__ __forceinline__ void r2c_paired_epilogue(const cf (&v)[E], cf* __rest
             static_for<0, R>([&](auto u_) {
                 constexpr int u = decltype(u_)::value;
                 if constexpr (u < R / 2) {
-                    emit(v[A + u], pick(v[Bk + R - 1 - u], v[A + (R - u) % R]), p + u * STR,
-                         factor(Int<u * (32 / R)>{}, p + u * STR));                                // self: Y[u*STR] (u = 0: Y[0], Y[M])
+                    emit(v[A + u], pick(v[Bk + R - 1 - u], v[A + (R - u) % R]), u * STR,
+                         factor(Int<u * (32 / R)>{}, u * STR));                                    // self: Y[u*STR] (u = 0: Y[0], Y[M])
                 } else {
                     constexpr int w = u - R / 2;
-                    const int k = self ? STR / 2 + w * STR : p + u * STR;
+                    const int c = self ? STR / 2 + w * STR : u * STR;                              // (self: j = 0, so c is the bin itself)
                     cf f;
                     if constexpr (CONST_TW) {
                         // self: bin STR/2 + w*STR, factor W_64^(16/R + w*32/R) (wj = 1 there: the product is the constant itself)
                         constexpr int ks = 16 / R + w * (32 / R), kn = u * (32 / R);
                         f = cmul(wj, self ? make_float2(cos64(ks), -sin64(ks)) : make_float2(cos64(kn), -sin64(kn)));
                     } else {
-                        f = __ldg(table + (k << sh_real));
+                        f = table_at(tj, (unsigned) c, tstep);
                     }
-                    emit(pick(v[A + u], v[Bk + w]), pick(v[Bk + R - 1 - u], v[Bk + R - 1 - w]), k, f);
+                    emit(pick(v[A + u], v[Bk + w]), pick(v[Bk + R - 1 - u], v[Bk + R - 1 - w]), c, f);
                 }
             });
             if (self) {
                 const cf mid = v[A + R / 2];                                         // Z[M/2]
-                put_bin<AUDIO>(dst, M / 2, make_float2(2.0f * mid.x, -2.0f * mid.y));
+                put_at<AUDIO>(lo + M / 2, make_float2(2.0f * mid.x, -2.0f * mid.y));
             }
         } else {
             static_for<0, R>([&](auto u_) {
                 constexpr int u = decltype(u_)::value;
-                emit(v[A + u], v[Bk + R - 1 - u], p + u * STR, factor(Int<s * (32 / E) + u * (32 / R)>{}, p + u * STR));
+                emit(v[A + u], v[Bk + R - 1 - u], s * T + u * STR, factor(Int<s * (32 / E) + u * (32 / R)>{}, s * T + u * STR));
             });
         }
     });
@@ -445,8 +514,12 @@ struct Cfg {
     // real split / twist factors W_2M^k: from the table, or the thread's own W_2M^j times compile-time constants (see
     // r2c_paired_epilogue).  By measurement (real n = 2M): forward 128 .75 -> .79, 256 .85 -> .89, 16384 .72 -> .73;
     // inverse 64 .57 -> .59, 128 .73 -> .78, 256 .73 -> .75, 8192 .79 -> .80, 16384 .71 -> .72; slower elsewhere (spills).
+#ifdef CKB_RTWC_ALL      // development A/B builds: constant factors wherever the plan allows them / nowhere
+    static constexpr bool RTWC = CKB_RTWC_ALL != 0 && MODE_ != MODE_C2C && 32 % E_ == 0 && (MODE_ == MODE_C2R || 16 % (R2_ > 1 ? R2_ : R1_) == 0 || (E_ / (R2_ > 1 ? R2_ : R1_)) % 2 != 0 || M_ == 512);
+#else
     static constexpr bool RTWC = MODE_ == MODE_R2C ? (M_ == 64 || M_ == 128 || M_ == 8192)
                                : MODE_ == MODE_C2R ? (M_ == 32 || M_ == 64 || M_ == 128 || M_ == 4096 || M_ == 8192) : false;
+#endif
     static constexpr int LOGPAD = ilog2(R0);
     // complex slots per group (+ slot M for the real modes).  Plans with several groups per half-warp (T = 4, 8) need a
     // group pitch of 12 resp. 8 (mod 16) 8-byte words: with the raw pitch (6 or 10 mod 16) the groups of a half-warp land on
@@ -523,10 +596,13 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
     cf wj = make_float2(1.f, 0.f);
     if constexpr (C::RTWC) wj = __ldg(p.table + (j << sh_real));
     static_assert(!C::RTWC || 32 % E == 0, "split / twist factors are multiples of 1/64 turn");
+    const cf* __restrict__ tab_j = p.table + ((long long) j << sh_real);
+    const unsigned tab_step = table_step_bytes(sh_real);
     auto real_factor = [&](auto i_, int k) -> cf {                 // forward W_2M^k, k = j + i*T
         if constexpr (C::RTWC) return cmul_w64<decltype(i_)::value * (32 / E)>(wj);
-        else                   return __ldg(p.table + (k << sh_real));
+        else                   return table_at(tab_j, (unsigned) (decltype(i_)::value * T), tab_step);
     };
+    (void) tab_j; (void) tab_step;
     (void) real_factor;
 
     cf twb[TwSplit<R1>::NB];

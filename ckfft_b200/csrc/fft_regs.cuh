@@ -94,9 +94,15 @@ __device__ __forceinline__ cf fma2(cf a, cf b, cf c)
 __device__ __forceinline__ cf swp(cf a) { return make_float2(a.y, a.x); }
 __device__ __forceinline__ cf bc(float x) { return make_float2(x, x); }
 
+// CKB_PACKED_CMUL: packed arithmetic in the complex multiplications only (twiddles, split / twist factors).  Their operands
+// are register pairs that 64-bit loads already aligned, so this costs no extra registers, unlike the packed butterflies.
+#ifndef CKB_PACKED_CMUL
+#define CKB_PACKED_CMUL CKB_PACKED_MATH
+#endif
+
 __device__ __forceinline__ cf cmul(cf a, cf w)
 {
-#if CKB_PACKED_MATH
+#if CKB_PACKED_CMUL
     const cf u = mul2(bc(w.y), swp(a));                              // (w.y a.y, w.y a.x)
     return fma2(bc(w.x), a, make_float2(-u.x, u.y));                 // (w.x a.x - w.y a.y, w.x a.y + w.y a.x)
 #else

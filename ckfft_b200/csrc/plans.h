@@ -37,8 +37,11 @@
 // the split, measured .686 without and .672 with it and keeps the LUT.
 #define CKB_SPLIT_PREFETCH_PLANS(X) \
     X(16384, 32, 32, 32, 16,  1, 1, 1)
+#ifndef CKB_TWR_16K_REAL      /* development A/B builds */
+#define CKB_TWR_16K_REAL 0
+#endif
 #define CKB_SPLIT_PREFETCH_PLANS_R2C(X) \
-    X(16384, 32, 32, 32, 16,  1, 1, 0)
+    X(16384, 32, 32, 32, 16,  1, 1, CKB_TWR_16K_REAL)
 
 // In-place prefetch variants (Cfg::PF == PF_INPLACE), complex transforms only.  Measured on B200 (fraction of
 // the 6.55 TB/s copy peak, without -> with): 256 .89->.94, 512 .87->.95, 2048 .90->.95, 4096 .66->.95,
@@ -73,7 +76,7 @@
     X(2048,  32, 32, 32,  2,  4, 2, 1) \
     X(4096,  32, 32, 32,  4,  2, 2, 1) \
     X(8192,  32, 32, 32,  8,  1, 2, 1) \
-    X(16384, 32, 32, 32, 16,  1, 1, 0)
+    X(16384, 32, 32, 32, 16,  1, 1, CKB_TWR_16K_REAL)
 
 #define CKB_MAX_SINGLE_PASS 16384   /* largest complex length done in one launch */
 #define CKB_MAX_TABLE 32768         /* device twiddle table W_Nt^k covers real n up to this in one pass */

@@ -270,3 +270,70 @@ def test_real_16_points_odd_strides_take_the_thread_per_transform_kernels(ctx_bi
     assert lib.CkFftRealForwardBatchAsync(ctx_big.handle, n, xin.data_ptr(), spec.data_ptr(), batch, pin, 0, None) == 1, ck.last_error()
     torch.cuda.synchronize()
     assert rel_rms(spec.cpu().numpy(), orc_big.real_forward(x)) <= tolerance(n)
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-pass lengths (> 16384 complex points) with padded rows: one transform per launch sequence (api.cu)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("log2n", [15, 16, 18, 21])
+def test_large_complex_rows_strided(log2n):
+    """padded input and output rows above the single-pass limit, bit-identical to the dense call; the padding stays untouched"""
+    lib = _lib.load()
+    n = 1 << log2n
+    batch = 3
+    pin, pout = n + 6, n + 3                      # 16-byte aligned input rows (dataflow kernel) / 8-byte aligned output rows
+    rng = np.random.default_rng(log2n)
+    with ck.Context(n, ck.BOTH) as ctx:
+        x = torch.from_numpy(uniform_complex(rng, (batch, n))).cuda()
+        xin = torch.zeros((batch, pin), dtype=torch.complex64, device="cuda")
+        xin[:, :n] = x
+        for inverse in (False, True):
+            want = ctx.complex_inverse(x) if inverse else ctx.complex_forward(x)
+            out = torch.full((batch, pout), 7.0 + 0j, dtype=torch.complex64, device="cuda")
+            fn = lib.CkFftComplexInverseBatchAsync if inverse else lib.CkFftComplexForwardBatchAsync
+            assert fn(ctx.handle, n, xin.data_ptr(), out.data_ptr(), batch, pin, pout, None) == 1, ck.last_error()
+            torch.cuda.synchronize()
+            assert np.array_equal(bits(out[:, :n].contiguous()), bits(want)), (log2n, inverse)
+            assert bool((out[:, n:] == 7.0).all()), "padding between rows was written"
+        # rows that start 8 bytes off a 16-byte boundary (odd pitch): the plain-load tile kernels
+        xodd = torch.zeros((batch, n + 1), dtype=torch.complex64, device="cuda")
+        xodd[:, :n] = x
+        out = torch.empty((batch, n + 1), dtype=torch.complex64, device="cuda")
+        assert lib.CkFftComplexForwardBatchAsync(ctx.handle, n, xodd.data_ptr(), out.data_ptr(), batch, n + 1, n + 1, None) == 1, ck.last_error()
+        torch.cuda.synchronize()
+        assert rel_rms(out[:, :n].cpu().numpy(), ctx.complex_forward(x).cpu().numpy()) <= tolerance(n)
+
+
+@pytest.mark.parametrize("n", [1 << 16, 1 << 17, 1 << 19, 1 << 22])
+def test_large_real_rows_strided_and_in_place(n):
+    lib = _lib.load()
+    batch = 3
+    bins = n // 2 + 1
+    pin, pspec, pout = n + 4, bins + 2, n + 6
+    rng = np.random.default_rng(n)
+    with ck.Context(n, ck.BOTH) as ctx:
+        x = torch.from_numpy(rng.uniform(-1, 1, (batch, n)).astype(np.float32)).cuda()
+        want = ctx.real_forward(x)
+        xin = torch.zeros((batch, pin), dtype=torch.float32, device="cuda")
+        xin[:, :n] = x
+        spec = torch.full((batch, pspec), 7.0 + 0j, dtype=torch.complex64, device="cuda")
+        assert lib.CkFftRealForwardBatchAsync(ctx.handle, n, xin.data_ptr(), spec.data_ptr(), batch, pin, pspec, None) == 1, ck.last_error()
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(spec[:, :bins].contiguous()), bits(want)), n
+        assert bool((spec[:, bins:] == 7.0).all()), "padding between spectrum rows was written"
+        back_want = ctx.real_inverse(want, n)
+        back = torch.full((batch, pout), 7.0, dtype=torch.float32, device="cuda")
+        assert lib.CkFftRealInverseBatchAsync(ctx.handle, n, spec.data_ptr(), back.data_ptr(), batch, pspec, pout, None) == 1, ck.last_error()
+        torch.cuda.synchronize()
+        assert rel_rms(back[:, :n].cpu().numpy(), back_want.cpu().numpy()) <= tolerance(n)
+        assert bool((back[:, n:] == 7.0).all()), "padding between sample rows was written"
+        # in place: rows of n + 2 floats = n/2 + 1 complex values, forward then inverse over the same bytes
+        buf = torch.zeros((batch, n + 2), dtype=torch.float32, device="cuda")
+        buf[:, :n] = x
+        assert lib.CkFftRealForwardBatchAsync(ctx.handle, n, buf.data_ptr(), buf.data_ptr(), batch, n + 2, bins, None) == 1, ck.last_error()
+        torch.cuda.synchronize()
+        got = buf.view(torch.complex64)
+        assert rel_rms(got.cpu().numpy(), want.cpu().numpy()) <= tolerance(n)
+        assert lib.CkFftRealInverseBatchAsync(ctx.handle, n, buf.data_ptr(), buf.data_ptr(), batch, bins, n + 2, None) == 1, ck.last_error()
+        torch.cuda.synchronize()
+        assert rel_rms(buf[:, :n].cpu().numpy() / n, x.cpu().numpy()) <= tolerance(n)
