@@ -182,12 +182,12 @@ __device__ __forceinline__ int bfly_index(int j, int q)
 // One Stockham stage = gather + math + scatter over the E register values of a thread.  They are
 // separate so the kernel can put a group barrier between a shared-memory gather and the scatter
 // that reuses the same buffer.
-template <int M, int T, int E, int R, int LOGPAD, int SRC, bool PAIRED = false>
+template <int M, int T, int E, int R, int LOGPAD, int SRC, bool PAIRED = false, bool LIN = true>
 __device__ __forceinline__ void stage_gather(cf (&v)[E], const cf* __restrict__ gsrc, const cf* xb, int j, bool valid)
 {
     constexpr int B = E / R;      // butterflies per thread
     constexpr int STR = M / R;    // distance between the R inputs of one butterfly
-    constexpr int PADW = 1 << LOGPAD;
+    constexpr int PADW = LIN ? 1 << LOGPAD : (1 << 30);     // !LIN (Cfg::LIN, by measurement): every padded index on its own
     static_assert(B * R == E, "radix must divide the per-thread element count");
     static_for<0, B>([&](auto q_) {
         constexpr int q = decltype(q_)::value;
@@ -291,12 +291,12 @@ __device__ __forceinline__ void stage_math(cf (&v)[E], const cf* lut, const cf* 
     static_for<0, B>([&](auto q_) { fft_regs<R, decltype(q_)::value * R, INV>(v); });
 }
 
-template <int M, int T, int E, int R, int NS, int LOGPAD, int DST>
+template <int M, int T, int E, int R, int NS, int LOGPAD, int DST, bool LIN = true>
 __device__ __forceinline__ void stage_scatter(const cf (&v)[E], cf* __restrict__ gdst, cf* xb, int j, bool valid)
 {
     constexpr int B = E / R;
     constexpr int STR = M / R;
-    constexpr int PADW = 1 << LOGPAD;
+    constexpr int PADW = LIN ? 1 << LOGPAD : (1 << 30);
     static_assert(DST != DST_GLOBAL || NS * R == M, "only the last stage writes global memory");
     static_for<0, B>([&](auto q_) {
         constexpr int q = decltype(q_)::value;
@@ -517,10 +517,20 @@ struct Cfg {
 #ifdef CKB_RTWC_ALL      // development A/B builds: constant factors wherever the plan allows them / nowhere
     static constexpr bool RTWC = CKB_RTWC_ALL != 0 && MODE_ != MODE_C2C && 32 % E_ == 0 && (MODE_ == MODE_C2R || 16 % (R2_ > 1 ? R2_ : R1_) == 0 || (E_ / (R2_ > 1 ? R2_ : R1_)) % 2 != 0 || M_ == 512);
 #else
-    static constexpr bool RTWC = MODE_ == MODE_R2C ? (M_ == 64 || M_ == 128 || M_ == 8192)
-                               : MODE_ == MODE_C2R ? (M_ == 32 || M_ == 64 || M_ == 128 || M_ == 4096 || M_ == 8192) : false;
+    // round 2 (leaner addressing, registers to spare): forward 4096 .84 -> .89, 16384 .70 -> .73; inverse 2048 .91 -> .92, 16384 .53 -> .70
+    static constexpr bool RTWC = MODE_ == MODE_R2C ? (M_ == 64 || M_ == 128 || M_ == 4096 || M_ == 8192 || M_ == 16384)
+                               : MODE_ == MODE_C2R ? (M_ == 32 || M_ == 64 || M_ == 128 || M_ == 2048 || M_ == 4096 || M_ == 8192 || M_ == 16384) : false;
 #endif
     static constexpr int LOGPAD = ilog2(R0);
+    // exchange-buffer addresses as one base + compile-time offsets (see padoff).  CKB_LEGACY_SIZES: plans that keep the
+    // per-element padded indices (development A/B switch)
+    // Measured exception: the complex 2048-point kernel (in-place prefetch, four groups of two warps) runs at 0.96 of the copy peak
+    // with the per-element indices and at 0.84-0.86 with the lean ones -- ptxas then schedules the stage-0 loads just in time
+    // (96 instead of 128 registers) and the groups spend 39 % instead of 26 % of their time waiting for their row.
+#ifndef CKB_LEGACY_SIZES
+#define CKB_LEGACY_SIZES (MODE_ == MODE_C2C && M_ == 2048 && !PLANAR_)
+#endif
+    static constexpr bool LIN = !(CKB_LEGACY_SIZES);
     // complex slots per group (+ slot M for the real modes).  Plans with several groups per half-warp (T = 4, 8) need a
     // group pitch of 12 resp. 8 (mod 16) 8-byte words: with the raw pitch (6 or 10 mod 16) the groups of a half-warp land on
     // each other's banks -- 4 to 8 conflicting lanes per exchange request (tools/bank_model.py, tests/test_bank_model.py).
@@ -712,7 +722,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
                 xb[padidx<LOGPAD>(M / 2)] = make_float2(2.0f * y.x, -2.0f * y.y);
             }
             group_sync<T>(g);
-            stage_gather<M, T, E, R0, LOGPAD, SRC_XBUF>(v, src, xb, j, valid);
+            stage_gather<M, T, E, R0, LOGPAD, SRC_XBUF, false, C::LIN>(v, src, xb, j, valid);
             group_sync<T>(g);
         } else if constexpr (C::PF == PF_SPLIT) {
             static_assert(E == R0, "one stage-0 butterfly per thread");
@@ -764,10 +774,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
         }
         stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j);
         constexpr bool PAIR1 = C::PAIRED && C::NSTAGE == 2;     // last stage of a two-stage real-forward plan
-        stage_scatter<M, T, E, R0, 1, LOGPAD, DST_XCHG>(v, dst, xb, j, valid);
+        stage_scatter<M, T, E, R0, 1, LOGPAD, DST_XCHG, C::LIN>(v, dst, xb, j, valid);
         group_sync<T>(g);
         // ---- stage 1 (Ns = R0) ----
-        stage_gather<M, T, E, R1, LOGPAD, SRC_XBUF, PAIR1>(v, src, xb, j, valid);
+        stage_gather<M, T, E, R1, LOGPAD, SRC_XBUF, PAIR1, C::LIN>(v, src, xb, j, valid);
         if constexpr (C::PF == PF_INPLACE && C::NSTAGE == 2) { group_sync<T>(g); issue_next(item); }
         if constexpr (C::TWR) stage_math_regs<E, R1, INV>(v, twb);
         else                  stage_math<T, E, R1, R0, INV, TW_LUT, PAIR1>(v, lut1, p.table, 0, j);
@@ -776,7 +786,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
                 r2c_paired_epilogue<M, T, E, R1, C::AUDIO, C::RTWC>(v, dst, p.table, sh_real, wj, j, valid);
             } else if constexpr (MODE == MODE_R2C) {
                 group_sync<T>(g);
-                stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XNAT>(v, dst, xb, j, valid);
+                stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XNAT, C::LIN>(v, dst, xb, j, valid);
             } else if constexpr (C::PLANAR) {
                 scatter_planar<M, T, E, R1>(v, reinterpret_cast<float*>(p.out) + item * p.out_stride, p.out_im + item * p.out_stride, j, valid);
             } else {
@@ -784,10 +794,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
             }
         } else {
             group_sync<T>(g);
-            stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XCHG>(v, dst, xb, j, valid);
+            stage_scatter<M, T, E, R1, R0, LOGPAD, DST_XCHG, C::LIN>(v, dst, xb, j, valid);
             group_sync<T>(g);
             // ---- stage 2 (Ns = R0*R1) ----
-            stage_gather<M, T, E, R2, LOGPAD, SRC_XBUF, C::PAIRED>(v, src, xb, j, valid);
+            stage_gather<M, T, E, R2, LOGPAD, SRC_XBUF, C::PAIRED, C::LIN>(v, src, xb, j, valid);
             if constexpr (C::PF == PF_INPLACE) { group_sync<T>(g); issue_next(item); }
             if constexpr (C::PF == PF_SPLIT) { group_sync<T>(g); issue_half(item + (long long) gridDim.x * G, 1); }
             if constexpr (C::POW2) stage_math_pow<E, R2, INV>(v, pw);
@@ -796,7 +806,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
                 r2c_paired_epilogue<M, T, E, R2, C::AUDIO, C::RTWC>(v, dst, p.table, sh_real, wj, j, valid);
             } else if constexpr (MODE == MODE_R2C) {
                 group_sync<T>(g);
-                stage_scatter<M, T, E, R2, R0 * R1, LOGPAD, DST_XNAT>(v, dst, xb, j, valid);
+                stage_scatter<M, T, E, R2, R0 * R1, LOGPAD, DST_XNAT, C::LIN>(v, dst, xb, j, valid);
             } else if constexpr (C::PLANAR) {
                 scatter_planar<M, T, E, R2>(v, reinterpret_cast<float*>(p.out) + item * p.out_stride, p.out_im + item * p.out_stride, j, valid);
             } else {

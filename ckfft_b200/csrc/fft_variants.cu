@@ -83,6 +83,28 @@ static cudaError_t launch_cfg(const KernelParams& p, cudaStream_t s)
 
 cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
 {
+    // development A/B builds (tools/exp_build.sh): -DCKB_EXP_A_M=2048 -DCKB_EXP_A_R2=2 -DCKB_EXP_A_G=3 -DCKB_EXP_A_MINB=2
+    // -DCKB_EXP_A_TWR=1 -DCKB_EXP_A_PF=PF_DOUBLE (and _B_) route one length to an experimental three-stage plan (aligned rows)
+#ifndef CKB_EXP_A_E
+#define CKB_EXP_A_E 32
+#define CKB_EXP_A_R0 32
+#define CKB_EXP_A_R1 32
+#endif
+#ifndef CKB_EXP_B_E
+#define CKB_EXP_B_E 32
+#define CKB_EXP_B_R0 32
+#define CKB_EXP_B_R1 32
+#endif
+#if defined(CKB_EXP_A_M) && CKB_VARIANT != 3 && CKB_VARIANT < 5
+    if (((uintptr_t) p.in & 15) == 0 && (p.in_stride & 1) == 0) {
+        if (M == CKB_EXP_A_M)
+            return launch_cfg<Cfg<CKB_EXP_A_M, CKB_EXP_A_E, CKB_EXP_A_R0, CKB_EXP_A_R1, CKB_EXP_A_R2, CKB_EXP_A_G, kInv, kMode, CKB_EXP_A_MINB, CKB_EXP_A_PF, CKB_EXP_A_TWR != 0, kAudio>>(p, s);
+#ifdef CKB_EXP_B_M
+        if (M == CKB_EXP_B_M)
+            return launch_cfg<Cfg<CKB_EXP_B_M, CKB_EXP_B_E, CKB_EXP_B_R0, CKB_EXP_B_R1, CKB_EXP_B_R2, CKB_EXP_B_G, kInv, kMode, CKB_EXP_B_MINB, CKB_EXP_B_PF, CKB_EXP_B_TWR != 0, kAudio>>(p, s);
+#endif
+    }
+#endif
 #if CKB_VARIANT != 3 && CKB_VARIANT < 5
     // bulk copies need 16-byte aligned rows
     if (prefetch_mode() && ((uintptr_t) p.in & 15) == 0 && (p.in_stride & 1) == 0) {
@@ -97,28 +119,41 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
 #endif
 #if CKB_VARIANT <= 1
     if (prefetch_mode() && ((uintptr_t) p.in & 15) == 0 && (p.in_stride & 1) == 0) {
+        switch (M) {           // split prefetch where the plan table has it, else in place
+#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_SPLIT, TWR_ != 0, kAudio>>(p, s);
+            CKB_SPLIT_PREFETCH_PLANS_C2C(X)
+#undef X
+            default: break;
+        }
         switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
     case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0, kAudio>>(p, s);
             CKB_INPLACE_PREFETCH_PLANS(X)
 #undef X
+            default: break;
+        }
+    }
+#elif CKB_VARIANT == 2
+    if (prefetch_mode() && ((uintptr_t) p.in & 15) == 0 && (p.in_stride & 1) == 0) {
+        switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
     case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_SPLIT, TWR_ != 0, kAudio>>(p, s);
-            CKB_SPLIT_PREFETCH_PLANS(X)
+            CKB_SPLIT_PREFETCH_PLANS_R2C(X)
 #undef X
             default: break;
         }
     }
-#elif CKB_VARIANT == 2 || CKB_VARIANT == 4
+#elif CKB_VARIANT == 4
     if (prefetch_mode() && ((uintptr_t) p.in & 15) == 0 && (p.in_stride & 1) == 0) {
         switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
     case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0, kAudio>>(p, s);
-            CKB_INPLACE_PREFETCH_PLANS_R2C(X)
+            CKB_INPLACE_PREFETCH_PLANS_AUDIO(X)
 #undef X
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
     case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_SPLIT, TWR_ != 0, kAudio>>(p, s);
-            CKB_SPLIT_PREFETCH_PLANS_R2C(X)
+            CKB_SPLIT_PREFETCH_PLANS_AUDIO(X)
 #undef X
             default: break;
         }

@@ -28,20 +28,38 @@
 #define CKB_PREFETCH_PLANS(X) \
     X(1024,  32, 32, 32,  1,  4, 3, 1)
 
-// 16384 points (Cfg::PF == PF_SPLIT): one transform fills the register file of an SM, so the only way to overlap
-// its HBM traffic with arithmetic is a prefetched successor in shared memory; a whole second row does not fit next to
-// the exchange buffer, so the row is prefetched in two halves (see fft_kernel.cuh).  0.64 -> 0.70 of the copy peak.
-// (A half-width exchange buffer -- real parts, then imaginary parts -- with a full staged row measured 0.67.)
-// Stage-1 twiddles from register bases (TWR) take 31 LUT reads per thread and transform off the shared-memory port:
-// complex .70 -> .77 (it costs 96 bytes of spills at the 128-register cap); the real-forward kernel, which also carries
-// the split, measured .686 without and .672 with it and keeps the LUT.
+// Split prefetch (Cfg::PF == PF_SPLIT): the lower half of a group's NEXT row is fetched into a half-row staging buffer as
+// soon as stage 0 has gathered the current one (in flight for the whole transform), the upper half into the exchange buffer
+// once the last stage has gathered.  Introduced for 16384 points (one transform fills the register file of an SM, a whole
+// second row does not fit next to the exchange buffer: 0.64 -> 0.70 of the copy peak; stage-1 twiddles from register bases,
+// TWR, on top: .70 -> .77).
+// Round 2: ONE CTA per SM with several groups (G x T = 384 .. 512 threads, MINB = 1) sharing one copy of the twiddle LUTs
+// beats two CTAs with in-place prefetch, whose load is only in flight during the short last stage (ncu: 26-39 % of the
+// stall samples on the mbarrier wait).  Measured (tools/exp_build.sh, fraction of the copy peak, in-place -> split):
+//   C2C 4096 (G = 3, LUT)  .88-.95 -> .995     C2C 8192 (G = 2, TWR)  .88 -> .97      C2C 2048 (G = 6) .96 -> .88 (stays in place)
+//   R2C M = 2048 (G = 6, LUT) .84-.90 -> .945 (config 3: .93 -> .96)      R2C M = 4096 (G = 3, TWR) .88 -> .93
 #define CKB_SPLIT_PREFETCH_PLANS(X) \
     X(16384, 32, 32, 32, 16,  1, 1, 1)
-#ifndef CKB_TWR_16K_REAL      /* development A/B builds */
-#define CKB_TWR_16K_REAL 0
-#endif
+#define CKB_SPLIT_PREFETCH_PLANS_C2C(X) \
+    X(4096,  32, 32, 32,  4,  3, 1, 0) \
+    X(8192,  32, 32, 32,  8,  2, 1, 1) \
+    X(16384, 32, 32, 32, 16,  1, 1, 1)
+// (16384 real forward: TWR measured .686 without and .672 with it and keeps the LUT)
 #define CKB_SPLIT_PREFETCH_PLANS_R2C(X) \
-    X(16384, 32, 32, 32, 16,  1, 1, CKB_TWR_16K_REAL)
+    X(2048,  32, 32, 32,  2,  6, 1, 0) \
+    X(4096,  32, 32, 32,  4,  3, 1, 1) \
+    X(8192,  32, 32, 32,  8,  2, 1, 0) \
+    X(16384, 32, 32, 32, 16,  1, 1, 0)
+// (R2C M = 8192, real n = 16384: in place G = 1 x 2 CTAs, TWR .75; split G = 1 x 2 CTAs, TWR .74; split G = 2, TWR .61 -- the
+//  register twiddle bases next to the constant split factors spill; split G = 2 with the LUT .815)
+// The audio front end (window + real forward + power spectrum) is issue-bound and wants the 16 warps per SM of the two-CTA
+// in-place plans: 2048 points in place .72, split G = 6 .66, split G = 8 .65, in place G = 5 x 2 CTAs (102 registers) .52.
+#define CKB_INPLACE_PREFETCH_PLANS_AUDIO(X) \
+    X(2048,  32, 32, 32,  2,  4, 2, 1) \
+    X(4096,  32, 32, 32,  4,  2, 2, 1) \
+    X(8192,  32, 32, 32,  8,  1, 2, 1)
+#define CKB_SPLIT_PREFETCH_PLANS_AUDIO(X) \
+    X(16384, 32, 32, 32, 16,  1, 1, 0)
 
 // In-place prefetch variants (Cfg::PF == PF_INPLACE), complex transforms only.  Measured on B200 (fraction of
 // the 6.55 TB/s copy peak, without -> with): 256 .89->.94, 512 .87->.95, 2048 .90->.95, 4096 .66->.95,
@@ -61,12 +79,8 @@
     X(2048,  32, 32, 32,  2,  4, 2, 0) \
     X(4096,  32, 32, 32,  4,  2, 2, 0) \
     X(8192,  32, 32, 32,  8,  1, 2, 1)
-// Real-forward in-place prefetch (needs the register split, i.e. an even number of last-stage butterflies).
-// (register stage twiddles, TWR: 2048 .87 -> .89, 4096 .77 -> .80; real inverse .83 -> .85, .76 -> .79)
-#define CKB_INPLACE_PREFETCH_PLANS_R2C(X) \
-    X(2048,  32, 32, 32,  2,  4, 2, 1) \
-    X(4096,  32, 32, 32,  4,  2, 2, 1) \
-    X(8192,  32, 32, 32,  8,  1, 2, 1)
+// (Real-forward transforms of 4096 .. 16384 points used in-place prefetch with register stage twiddles in round 1 --
+// 2048 .87 -> .89, 4096 .77 -> .80 -- and moved to the multi-group split prefetch above in round 2.)
 
 // Real-inverse in-place prefetch (rows are bulk-copied from the 16-byte boundary below them, twisted in place).
 // (16384: the row does not leave room for a second buffer and the split prefetch needs the halves at different times,
@@ -76,7 +90,7 @@
     X(2048,  32, 32, 32,  2,  4, 2, 1) \
     X(4096,  32, 32, 32,  4,  2, 2, 1) \
     X(8192,  32, 32, 32,  8,  1, 2, 1) \
-    X(16384, 32, 32, 32, 16,  1, 1, CKB_TWR_16K_REAL)
+    X(16384, 32, 32, 32, 16,  1, 1, 1)      /* round 2: register twiddles + constant twist factors .53 -> .72 */
 
 #define CKB_MAX_SINGLE_PASS 16384   /* largest complex length done in one launch */
 #define CKB_MAX_TABLE 32768         /* device twiddle table W_Nt^k covers real n up to this in one pass */

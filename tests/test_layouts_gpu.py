@@ -336,4 +336,4 @@ def test_large_real_rows_strided_and_in_place(n):
         assert rel_rms(got.cpu().numpy(), want.cpu().numpy()) <= tolerance(n)
         assert lib.CkFftRealInverseBatchAsync(ctx.handle, n, buf.data_ptr(), buf.data_ptr(), batch, bins, n + 2, None) == 1, ck.last_error()
         torch.cuda.synchronize()
-        assert rel_rms(buf[:, :n].cpu().numpy() / n, x.cpu().numpy()) <= tolerance(n)
+        assert rel_rms(buf[:, :n].cpu().numpy() / (2 * n), x.cpu().numpy()) <= tolerance(n)      # inverse(forward(x)) = 2 n x
