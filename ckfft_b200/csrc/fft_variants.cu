@@ -176,6 +176,7 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
     }
 #endif
 #if CKB_VARIANT == 3
+    KernelParams rest = p;          // what the plain-load kernels below still have to do
     if (prefetch_mode() && p.batch > 0 && ((uintptr_t) p.in & 15) == 0) {      // (first row: nothing to read below it)
         // Rows start on 8-byte boundaries; the kernel copies M+2 values from the 16-byte boundary below each row.
         // If that would run past the end of the LAST row (its pad is 0 and rows are dense), that row goes to the
@@ -185,33 +186,54 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
         KernelParams head = p;
         if (last_overruns) head.batch = p.batch - 1;
         cudaError_t e = cudaErrorInvalidValue;
-        switch (M) {
+        switch (M) {           // split prefetch where the plan table has it, else in place
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: e = launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0, kAudio>>(head, s); break;
-            CKB_INPLACE_PREFETCH_PLANS_C2R(X)
+    case M_: e = launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_SPLIT, TWR_ != 0, kAudio>>(head, s); break;
+            CKB_SPLIT_PREFETCH_PLANS_C2R(X)
 #undef X
             default: break;
         }
-        if (e == cudaSuccess) {
-            if (!last_overruns) return cudaSuccess;
-            KernelParams tail = p;
-            tail.in = p.in + (p.batch - 1) * p.in_stride;
-            tail.out = p.out + (p.batch - 1) * p.out_stride;
-            tail.batch = 1;
+        if (e == cudaErrorInvalidValue) {
             switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0, kAudio>>(tail, s);
+    case M_: e = launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0, kAudio>>(head, s); break;
+                CKB_INPLACE_PREFETCH_PLANS_C2R(X)
+#undef X
+                default: break;
+            }
+        }
+        if (e == cudaSuccess) {
+            if (!last_overruns) return cudaSuccess;
+            // the last row through the plain-load kernel of the SAME plan (same twiddle source, so the same bits whichever
+            // rows a caller's chunking turns into last rows)
+            rest.in = p.in + (p.batch - 1) * p.in_stride;
+            rest.out = p.out + (p.batch - 1) * p.out_stride;
+            rest.batch = 1;
+            switch (M) {
+#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0, kAudio>>(rest, s);
+                CKB_SPLIT_PREFETCH_PLANS_C2R(X)
+#undef X
+                default: break;
+            }
+            switch (M) {
+#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0, kAudio>>(rest, s);
                 CKB_INPLACE_PREFETCH_PLANS_C2R(X)
 #undef X
                 default: return cudaErrorInvalidValue;
             }
+        } else if (e != cudaErrorInvalidValue) {
+            return e;
         }
-        if (e != cudaErrorInvalidValue) return e;
     }
+    const KernelParams& q = rest;
+#else
+    const KernelParams& q = p;
 #endif
     switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0, kAudio, kPlanar>>(p, s);
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0, kAudio, kPlanar>>(q, s);
         CKB_SINGLE_PASS_PLANS(X)
 #undef X
         default: return cudaErrorInvalidValue;
