@@ -548,11 +548,12 @@ struct Cfg {
     static constexpr int NPOW = POW2 ? (E / R2) * ilog2(R2) : 1;
     static constexpr int LUT2 = LUT2_SMEM ? (R2 - 1) * R0 * R1 : 0;   // stage 2: Ns = R0*R1
     static constexpr int XSLOTS = XBUF;                                      // complex slots of the exchange buffer
-    // (real inverse, split prefetch: each half is copied from a 16-byte boundary and holds M/2 + 2 values, see the C2R prologue)
-    static constexpr int GROUP_SLOTS = XSLOTS + (PF == PF_DOUBLE ? M : (PF == PF_SPLIT ? M / 2 + (MODE_ == MODE_C2R ? 2 : 0) : 0));   // exchange (+ staging) buffer
-    static_assert(PF_ != PF_SPLIT || (R2_ > 1 && (MODE_ == MODE_C2C || MODE_ == MODE_C2R || (MODE_ == MODE_R2C && (E_ / R2_) % 2 == 0))),
+    static constexpr int GROUP_SLOTS = XSLOTS + (PF == PF_DOUBLE ? M : (PF == PF_SPLIT ? M / 2 : 0));   // exchange (+ staging) buffer
+    // (Real inverse with split prefetch was built and measured in round 2 -- the twist evaluated straight from the two raw half
+    // rows, every pair by both of its owners: correct, .87 -> .89 at 4096 points, .78 -> .54 / .78 at 8192, .72 -> .67 at 16384,
+    // and no longer bit-identical to the pairwise kernels that take unaligned and last rows; removed again, see DESIGN.md.)
+    static_assert(PF_ != PF_SPLIT || (R2_ > 1 && (MODE_ == MODE_C2C || (MODE_ == MODE_R2C && (E_ / R2_) % 2 == 0))),
                   "split prefetch: three-stage plans whose last stage leaves the exchange buffer idle");
-    static_assert(PF_ != PF_SPLIT || MODE_ != MODE_C2R || E_ == R0_, "split prefetch, real inverse: one stage-0 butterfly per thread");
     static constexpr int SMEM_BYTES = 8 * (LUT1 + LUT2 + G * GROUP_SLOTS) + (PF ? 16 * G : 0);   // + two mbarriers per group
     static_assert(PF != PF_DOUBLE || MODE_ != MODE_C2R, "C2R prefetches in place (see the C2R prologue)");
     static_assert(PF != PF_INPLACE || MODE_ != MODE_R2C || ((E_ / (R2_ > 1 ? R2_ : R1_)) % 2 == 0 && M_ != 512),
@@ -658,17 +659,6 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
     (void) issue_next;
     // PF_SPLIT: half 0 = points [0, M/2) -> staging buffer, half 1 = points [M/2, M) -> exchange buffer
     auto issue_half = [&](long long row, int half) {
-        if constexpr (MODE == MODE_C2R) {
-            // half spectra: M + 1 values from an 8-byte boundary.  Both copies start on 16-byte boundaries: slots [0, M/2 + 2) and
-            // [M/2, M + 2) counted from the boundary at or below the row, so Y[k] sits in inb[k + pad] (k < M/2) or xb[k - M/2 + pad]
-            // (k >= M/2), pad = 0 or 1.  (The launcher keeps a last row whose over-copy would leave the array out of this kernel.)
-            if (j == 0 && row < p.batch) {
-                const cf* rsrc = reinterpret_cast<const cf*>(reinterpret_cast<uintptr_t>(p.in + row * p.in_stride) & ~uintptr_t(15));
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(half ? mbar_hi : mbar, (M / 2 + 2) * 8);
-                bulk_load(half ? xb : inb, rsrc + half * (M / 2), (M / 2 + 2) * 8, half ? mbar_hi : mbar, l2pol);
-            }
-        } else
         if (j == 0 && row < p.batch) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(half ? mbar_hi : mbar, M * 4);
@@ -694,39 +684,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_kernel(const KernelPa
         cf v[E];
 
         // ---- stage 0 (Ns = 1, no twiddles) ----
-        if constexpr (MODE == MODE_C2R && C::PF == PF_SPLIT) {
-            // Twist straight from the two raw half rows into this thread's stage-0 inputs: element i = j + t*T pairs with M - i,
-            // which another thread owns, so every thread reads its R0 elements AND their R0 mirrors and evaluates its own side
-            // of each pair (twice the twist arithmetic of the pairwise version, but no write-back, no second barrier and no
-            // re-read -- and the lower half row can be in flight for the whole transform).  Same operations per element as
-            // fft_real_default.cpp:65-111:  k = min(i, M - i), y0 = Y[k], y1 = Y[M-k], c = i conj(W_2M^k) (y0 - conj y1),
-            //   T[k] = (y0 + conj y1) + c,   T[M-k] = conj((y0 + conj y1) - c);   W_2M^(M-i) = -conj(W_2M^i).
-            static_assert(E == R0, "one stage-0 butterfly per thread");
-            if (valid) { mbar_wait(mbar, phase); mbar_wait(mbar_hi, phase); }
-            phase ^= 1u;
-            const int pad = (int) ((reinterpret_cast<uintptr_t>(src) >> 3) & 1);
-            const cf* ylo = inb + pad + j;                    // Y[j + c]      = ylo[c],   j + c <  M/2
-            const cf* yhi = xb + pad + j;                     // Y[j + c]      = yhi[c - M/2],   j + c >= M/2
-            const cf* mlo = inb + pad + (M / 2 - j);          // Y[M - j - c]  = mlo[M/2 - c],   M - j - c <  M/2   (c > M/2 - j)
-            const cf* mhi = xb + pad + (M / 2 - j);           // Y[M - j - c]  = mhi[-c],        M - j - c >= M/2
-            static_for<0, R0>([&](auto t_) {
-                constexpr int t = decltype(t_)::value;
-                constexpr int c = t * T;
-                constexpr bool upper = t >= R0 / 2;           // i = j + c >= M/2
-                cf own, mir;
-                if constexpr (!upper) { own = ylo[c]; mir = mhi[-c]; }
-                else                  { own = yhi[c - M / 2]; mir = (t == R0 / 2) ? (j == 0 ? own : mlo[M / 2 - c]) : mlo[M / 2 - c]; }
-                const cf wi = real_factor(t_, j + c);          // forward W_2M^i
-                const cf y0 = upper ? mir : own, y1 = upper ? own : mir;
-                const cf w = upper ? make_float2(-wi.x, wi.y) : wi;                  // W_2M^k, k = min(i, M - i)
-                const cf sum = make_float2(y0.x + y1.x, y0.y - y1.y);
-                const cf dif = make_float2(y0.x - y1.x, y0.y + y1.y);
-                const cf cc = cmul(make_float2(w.y, w.x), dif);
-                v[bitrev<R0>(t)] = upper ? make_float2(sum.x - cc.x, -(sum.y - cc.y)) : make_float2(sum.x + cc.x, sum.y + cc.y);
-            });
-            group_sync<T>(g);                      // both half rows are consumed
-            issue_half(item + (long long) gridDim.x * G, 0);
-        } else if constexpr (MODE == MODE_C2R && C::PF == PF_INPLACE) {
+        if constexpr (MODE == MODE_C2R && C::PF == PF_INPLACE) {
             // The row was bulk-copied into the (dense) buffer; twist it in place -- a thread owns both slots of a
             // mirror pair -- then gather stage 0 from the dense layout.
             if (valid) mbar_wait(mbar, phase);

@@ -186,21 +186,12 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
         KernelParams head = p;
         if (last_overruns) head.batch = p.batch - 1;
         cudaError_t e = cudaErrorInvalidValue;
-        switch (M) {           // split prefetch where the plan table has it, else in place
-#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: e = launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_SPLIT, TWR_ != 0, kAudio>>(head, s); break;
-            CKB_SPLIT_PREFETCH_PLANS_C2R(X)
-#undef X
-            default: break;
-        }
-        if (e == cudaErrorInvalidValue) {
-            switch (M) {
+        switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
     case M_: e = launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0, kAudio>>(head, s); break;
-                CKB_INPLACE_PREFETCH_PLANS_C2R(X)
+            CKB_INPLACE_PREFETCH_PLANS_C2R(X)
 #undef X
-                default: break;
-            }
+            default: break;
         }
         if (e == cudaSuccess) {
             if (!last_overruns) return cudaSuccess;
@@ -209,13 +200,6 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
             rest.in = p.in + (p.batch - 1) * p.in_stride;
             rest.out = p.out + (p.batch - 1) * p.out_stride;
             rest.batch = 1;
-            switch (M) {
-#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0, kAudio>>(rest, s);
-                CKB_SPLIT_PREFETCH_PLANS_C2R(X)
-#undef X
-                default: break;
-            }
             switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
     case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_NONE, TWR_ != 0, kAudio>>(rest, s);

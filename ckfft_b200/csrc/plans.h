@@ -92,12 +92,5 @@
     X(8192,  32, 32, 32,  8,  1, 2, 1) \
     X(16384, 32, 32, 32, 16,  1, 1, 1)      /* round 2: register twiddles + constant twist factors .53 -> .72 */
 
-// Real-inverse split prefetch: the twist is evaluated straight from the two raw half rows (fft_kernel.cuh, C2R prologue; every
-// pair is evaluated by both of its owners).  Measured (in place -> split): M = 4096 (G = 3, TWR) .87 -> .89; M = 8192 (G = 2)
-// .78 -> .54 with register twiddles, .78 with the LUT; M = 16384 .72 -> .67 / .66: the doubled twist arithmetic and its
-// registers eat what the longer prefetch window gives, so only 4096 points use it.
-#define CKB_SPLIT_PREFETCH_PLANS_C2R(X) \
-    X(4096,  32, 32, 32,  4,  3, 1, 1)
-
 #define CKB_MAX_SINGLE_PASS 16384   /* largest complex length done in one launch */
 #define CKB_MAX_TABLE 32768         /* device twiddle table W_Nt^k covers real n up to this in one pass */
