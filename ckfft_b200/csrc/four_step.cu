@@ -90,13 +90,13 @@ bool pipe_enabled()
     return env_ll("CKFFT_B200_PIPE", 1) != 0 && tensor_map_encoder() != nullptr;   // read per call: tests flip it
 }
 
-template <int L0, int L1, int MINB, bool INV, int NBUF, int MODE = PIPE_C2C>
+template <int L0, int L1, int MINB, bool INV, int NBUF, int MODE = PIPE_C2C, bool SPLIT = false>
 static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const cf* table, int log2_nt, const BigTwiddles& tw,
                                    cudaStream_t s, long long out_stride = 0, long long in_stride = 0)
 {
     using A = typename PipeTile<L0, INV, KIND_COLUMN>::type;
     using B = typename PipeTile<L1, INV, KIND_LAST>::type;
-    using PC = PipeCfg<A, B, MINB, NBUF, MODE>;
+    using PC = PipeCfg<A, B, MINB, NBUF, MODE, SPLIT>;
     constexpr bool REAL = MODE == PIPE_R2C, TWIST = MODE == PIPE_C2R;
     auto kern = pipe_kernel<PC, A, B>;
     constexpr int CTA = PC::THREADS + 64;                    // consumers + loader warp + signaller warp
@@ -162,7 +162,7 @@ static cudaError_t launch_pipe_cfg(const cf* in, cf* out, long long batch, const
                 return cudaErrorNotSupported;              // the caller falls back to the separate twist pass
             }
         }
-    } else if (!make_tile_map(&tmap, in, batch * L0, L1, A::BOX_ROWS, A::C)) { cudaFreeAsync(ws, s); return cudaErrorInvalidValue; }
+    } else if (!make_tile_map(&tmap, in, batch * L0, L1, PC::BOXR, A::C)) { cudaFreeAsync(ws, s); return cudaErrorInvalidValue; }
 
     PipeParams p{};
     p.in = in; p.out = out; p.ring = (cf*) ws;
@@ -214,11 +214,17 @@ cudaError_t launch_pipe(bool inverse, int log2n, const cf* in, cf* out, long lon
     four_step_plan(log2n, &npass, L);
     if (npass != 2 || ((uintptr_t) in & 15)) return cudaErrorNotSupported;
     const bool two = env_ll("CKFFT_B200_PIPE_NBUF", 2) == 2 && L[1] <= 256;     // ping-pong tile buffers where three CTAs still fit (CKFFT_B200_PIPE_NBUF=1: A/B)
+    // one buffer + half-tile staging area for the 512 / 1024-point tile plans (CKFFT_B200_PIPE_SPLIT=0: A/B).  Measured, one
+    // buffer -> split: 2^18 .572 -> .591, 2^19 .551 -> .569, 2^20 .515 -> .534; 2^17 (256 x 512) .518 -> .503 and keeps one buffer
+    const bool split = env_ll("CKFFT_B200_PIPE_SPLIT", 1) != 0 && L[0] >= 512;
 #define X(L0_, L1_, MINB_) \
     if (L[0] == L0_ && L[1] == L1_) { \
         if (two && L1_ <= 256) \
             return inverse ? launch_pipe_cfg<L0_, L1_, MINB_, true, (L1_ <= 256 ? 2 : 1)>(in, out, batch, table, log2_nt, tw, s) \
                            : launch_pipe_cfg<L0_, L1_, MINB_, false, (L1_ <= 256 ? 2 : 1)>(in, out, batch, table, log2_nt, tw, s); \
+        if (split && L0_ >= 512) \
+            return inverse ? launch_pipe_cfg<L0_, L1_, MINB_, true, 1, PIPE_C2C, (L0_ >= 512)>(in, out, batch, table, log2_nt, tw, s) \
+                           : launch_pipe_cfg<L0_, L1_, MINB_, false, 1, PIPE_C2C, (L0_ >= 512)>(in, out, batch, table, log2_nt, tw, s); \
         return inverse ? launch_pipe_cfg<L0_, L1_, MINB_, true, 1>(in, out, batch, table, log2_nt, tw, s) \
                        : launch_pipe_cfg<L0_, L1_, MINB_, false, 1>(in, out, batch, table, log2_nt, tw, s); \
     }
@@ -236,9 +242,11 @@ cudaError_t launch_pipe_r2c(int log2m, const cf* in, cf* out, long long batch, l
     four_step_plan(log2m, &npass, L);
     if (npass != 2 || ((uintptr_t) in & 15)) return cudaErrorNotSupported;
     const bool two = env_ll("CKFFT_B200_PIPE_NBUF", 2) == 2 && L[1] <= 256;
+    const bool split = env_ll("CKFFT_B200_PIPE_SPLIT", 1) != 0 && L[0] >= 512;      // real forward: 2^19 .431 -> .438, 2^20 .362 -> .385
 #define X(L0_, L1_, MINB_) \
     if (L[0] == L0_ && L[1] == L1_) { \
         if (two && L1_ <= 256) return launch_pipe_cfg<L0_, L1_, MINB_, false, (L1_ <= 256 ? 2 : 1), PIPE_R2C>(in, out, batch, table, log2_nt, tw, s, out_stride); \
+        if (split && L0_ >= 512) return launch_pipe_cfg<L0_, L1_, MINB_, false, 1, PIPE_R2C, (L0_ >= 512)>(in, out, batch, table, log2_nt, tw, s, out_stride); \
         return launch_pipe_cfg<L0_, L1_, MINB_, false, 1, PIPE_R2C>(in, out, batch, table, log2_nt, tw, s, out_stride); \
     }
     CKB_PIPE_PLANS(X)

@@ -150,8 +150,15 @@ __device__ __forceinline__ cf pipe_twiddle(const PipeParams& p, unsigned c, unsi
 // A: column-pass plan (L0, C0 columns of the [L0][L1] problem per tile), B: last-pass plan (L1, C1 contiguous columns)
 enum PipeMode { PIPE_C2C = 0, PIPE_R2C = 1, PIPE_C2R = 2 };
 
-template <class A, class B, int MINB_, int NBUF_ = 1, int MODE_ = PIPE_C2C>
+// SPLIT_ (one tile buffer, NBUF = 1): the first half of the NEXT tile -- rows [0, L0/2) of a pass-1 tile, columns [0, C/2) of a
+// pass-2 tile -- is fetched into a half-tile staging area S of its own as soon as the consumers have read S, i.e. right
+// after their first barrier; the second half lands in the exchange buffer once they have drained it, as before.  The
+// 512- and 1024-point tile plans have no room for a second whole buffer (ping-pong), and with one buffer the tile copy was
+// only in flight during the last radix stage and the stores: 2 000 of 7 800 cycles per item spent waiting for it.
+template <class A, class B, int MINB_, int NBUF_ = 1, int MODE_ = PIPE_C2C, bool SPLIT_ = false>
 struct PipeCfg {
+    static constexpr bool SPLIT = SPLIT_;
+    static_assert(!SPLIT_ || (NBUF_ == 1 && MODE_ != PIPE_C2R), "split tile prefetch: one buffer; the real inverse keeps its paired tiles");
     // REAL: real forward transform of 2M points = this M-point complex transform + the split
     //   Y[k] = (Z[k] + conj Z[M-k]) - i W_2M^k (Z[k] - conj Z[M-k])        (src/ckfft/fft_real_default.cpp:13-63)
     // fused into pass 2: a tile holds C/2 columns c and their mirrors L0 - c (columns 0 and L0/2 mirror themselves),
@@ -190,10 +197,15 @@ struct PipeCfg {
     static constexpr int TWIST_W = A::C / 2 + 2;
     static constexpr int XT = MODE_ == PIPE_C2R ? 2 * A::L * TWIST_W : 0;
     static constexpr int XALL = (((XA > XB ? XA : XB) > XT ? (XA > XB ? XA : XB) : XT) + 15) & ~15;   // whole 128-byte lines
-    static constexpr int LUTA = A::LUT1, LUTB = B::LUT1;
-    static constexpr int SMEM_BYTES = 8 * (LUTA + LUTB + NBUF * XALL) + 384;
-    static_assert((XALL * 8) % 128 == 0, "tile buffer alignment");
+    static constexpr bool SHARE_LUT = SPLIT_ && A::L == B::L && A::R0 == B::R0 && A::R1 == B::R1;     // one copy of the stage LUT when both passes have the same plan
+    static constexpr int LUTA = A::LUT1, LUTB = SHARE_LUT ? 0 : B::LUT1;
+    static constexpr int TILE_A = A::L * A::C, TILE_B = B::L * B::C;       // dense (staged) tiles
+    static constexpr int SHALF = SPLIT_ ? (TILE_A > TILE_B ? TILE_A : TILE_B) / 2 : 0;
+    static constexpr int BOXR = SPLIT_ && A::BOX_ROWS > A::L / 2 ? A::L / 2 : A::BOX_ROWS;     // rows per TMA box of a pass-1 tile
+    static constexpr int SMEM_BYTES = 8 * (LUTA + LUTB + NBUF * XALL + SHALF) + 384;
+    static_assert((XALL * 8) % 128 == 0 && (SHALF * 8) % 128 == 0, "tile buffer alignment");
     static_assert(((LUTA + LUTB) * 8) % 128 == 0, "tile buffer alignment");
+    static_assert(!SPLIT_ || (A::R0 % 2 == 0 && B::C % 2 == 0 && (A::E / A::R0) * A::T == A::L / A::R0), "split tile prefetch: halves by butterfly input / by column");
 };
 
 template <class PC, class A, class B>
@@ -207,11 +219,13 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
 
     extern __shared__ __align__(128) unsigned char pipe_smem[];
     cf* lutA = reinterpret_cast<cf*>(pipe_smem);
-    cf* lutB = lutA + PC::LUTA;
-    cf* xall = lutB + PC::LUTB;
+    cf* lutB = PC::SHARE_LUT ? lutA : lutA + PC::LUTA;
+    cf* xall = lutA + PC::LUTA + PC::LUTB;
     constexpr int NBUF = PC::NBUF;
-    // control block (128 bytes behind the tile buffers)
-    unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(xall + NBUF * PC::XALL);   // [2] tile landed (TMA complete_tx)
+    cf* sbuf = xall + NBUF * PC::XALL;            // SPLIT: staging area of the first half tile
+    (void) sbuf;
+    // control block (128 bytes behind the tile buffers).  SPLIT: index 0 = the exchange buffer (second half tile), 1 = S (first half)
+    unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(xall + NBUF * PC::XALL + PC::SHALF);   // [2] tile landed (TMA complete_tx)
     unsigned long long* bar_free = bar_full + 2;       // [2] every consumer has drained the buffer (stage-1 gather done)
     unsigned long long* bar_stored = bar_full + 4;     // [4] ring: every consumer has issued its global stores of item k (k & 3)
     unsigned long long* bar_sig = bar_full + 8;        // [4] ring: the signaller has handled item k (k & 3)
@@ -313,18 +327,44 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
                 spin_until(p.done1 + prob, (unsigned) T1);
             }
         };
-        auto request = [&](unsigned long long t, unsigned k) {        // item number k of this CTA carries ticket t
-            const unsigned b = k % NBUF;
-            cf* stage = xall + b * PC::XALL;
+        // part 2: the whole tile into buffer k % NBUF.  SPLIT: part 0 = item descriptor + first half tile into S, part 1 = second
+        // half into the exchange buffer.
+        auto request = [&](unsigned long long t, unsigned k, int part) {        // item number k of this CTA carries ticket t
+            const unsigned b = PC::SPLIT ? (part == 0 ? 1u : 0u) : k % NBUF;
+            cf* stage = PC::SPLIT && part == 0 ? sbuf : xall + (PC::SPLIT ? 0u : b) * PC::XALL;
             unsigned long long* full = bar_full + b;
             if (t >= total) {                                          // sentinel: complete the phase without a copy
-                item_desc[k & 7u] = make_uint4(0u, 0u, 0u, 0u);
+                if (part != 1) item_desc[k & 7u] = make_uint4(0u, 0u, 0u, 0u);
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(full)) : "memory");
                 return;
             }
             int pass; long long prob; int c0;
             decode(t, pass, prob, c0);
-            item_desc[k & 7u] = make_uint4((unsigned) pass, (unsigned) prob, (unsigned) c0, (unsigned) (prob % p.ring_slots));
+            if (part != 1) item_desc[k & 7u] = make_uint4((unsigned) pass, (unsigned) prob, (unsigned) c0, (unsigned) (prob % p.ring_slots));
+            if constexpr (PC::SPLIT) {
+                if (pass == 1) {
+                    // rows [0, L0/2) or [L0/2, L0) of the [L0][C] tile
+                    constexpr int HR = L0 / 2;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(full, HR * A::C * 8);
+#pragma unroll
+                    for (int r0 = 0; r0 < HR; r0 += PC::BOXR)
+                        tensor_load_2d_hint(stage + r0 * A::C, &tmap_in, c0, (int) (prob * L0 + part * HR + r0), full, pol_stream);
+                } else {
+                    // columns [0, C/2) or [C/2, C) of the tile, L1 contiguous values each
+                    constexpr int HC = B::C / 2;
+                    asm volatile("fence.proxy.async;" ::: "memory");       // other CTAs' generic stores -> our async-proxy reads
+                    mbar_expect_tx(full, L1 * HC * 8);
+                    const cf* slot = p.ring + (prob % p.ring_slots) * N;
+                    if (!PC::REAL && (p.flags & 1)) {
+                        bulk_load(stage, slot + (long long) (c0 + part * HC) * L1, L1 * HC * 8, full, pol_keep);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < HC; ++g) bulk_load(stage + g * L1, slot + (long long) pass2_column(c0, part * HC + g) * L1, L1 * 8, full, pol_keep);
+                    }
+                }
+                return;
+            }
             if (pass == 1) {
                 if constexpr (PC::TWIST) {
                     // C/2 columns from ca and their C/2 mirror columns, as two [L0][C/2] halves of the buffer
@@ -367,7 +407,11 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
             const long long s1 = CKB_STAT_CLOCK();
             wait_deps(t);
             const long long s2 = CKB_STAT_CLOCK();
-            if (j >= (unsigned) NBUF) mbar_wait_parked(bar_free + j % NBUF, (j / NBUF - 1) & 1u);     // item j - NBUF has drained the buffer
+            if constexpr (PC::SPLIT) {
+                if (j >= 1u) mbar_wait_parked(bar_free + 1, (j - 1u) & 1u);                           // item j - 1 has read S
+            } else {
+                if (j >= (unsigned) NBUF) mbar_wait_parked(bar_free + j % NBUF, (j / NBUF - 1) & 1u);     // item j - NBUF has drained the buffer
+            }
             const long long s3 = CKB_STAT_CLOCK();
             if (j >= 4u) mbar_wait_parked(bar_sig + (j & 3u), ((j >> 2) - 1) & 1u);                  // item j - 4 has been signalled
             const long long s4 = CKB_STAT_CLOCK();
@@ -375,7 +419,13 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
             req_clock[j & 7u] = s4;
             CKB_STAT_ADD(10, s1 - s0); CKB_STAT_ADD(11, s2 - s1); CKB_STAT_ADD(12, s3 - s2); CKB_STAT_ADD(13, s4 - s3); CKB_STAT_ADD(14, 1);
 #endif
-            request(t, j);
+            if constexpr (PC::SPLIT) {
+                request(t, j, 0);
+                if (j >= 1u) mbar_wait_parked(bar_free, (j - 1u) & 1u);                               // item j - 1 has drained the exchange buffer
+                request(t, j, 1);
+            } else {
+                request(t, j, 2);
+            }
             if (t >= total) {
 #if CKB_PIPE_STATS
                 stat_flush();
@@ -392,6 +442,7 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
         cf* xb = xall + b * PC::XALL;                           // this item's buffer: staged tile first, exchange buffer after
         unsigned long long* bfree = bar_free + b;
         const long long c0clk = CKB_STAT_CLOCK();
+        if constexpr (PC::SPLIT) mbar_wait_parked(bar_full + 1, k & 1u);       // first half tile (S)
         mbar_wait_parked(bar_full + b, (k / NBUF) & 1u);
         const long long c1clk = CKB_STAT_CLOCK();
         const uint4 desc = item_desc[k & 7u];
@@ -484,10 +535,14 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
                     constexpr int q = decltype(q_)::value;
                     static_for<0, R0>([&](auto t_) {
                         constexpr int t = decltype(t_)::value;
+                        if constexpr (PC::SPLIT)      // rows below L/2 are in S, the others in the exchange buffer (t * STR0 = t * L / R0)
+                            v[q * R0 + bitrev<R0>(t)] = t < R0 / 2 ? sbuf[(j + q * T + t * STR0) * C + g] : xb[(j + q * T + (t - R0 / 2) * STR0) * C + g];
+                        else
                         v[q * R0 + bitrev<R0>(t)] = xb[(j + q * T + t * STR0) * C + g];
                     });
                 });
                 consumer_sync();                              // the staged tile is consumed: the buffer now serves the exchange
+                if constexpr (PC::SPLIT) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_free + 1)) : "memory");
             }
             stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, jj);
             stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xb + g * XBUF, jj, true);
@@ -540,14 +595,17 @@ __global__ void __launch_bounds__(PC::THREADS + 64, PC::MINB) pipe_kernel(const 
             }
             cf v[E];
             constexpr int B0 = E / R0, STR0 = L / R0;
+            const cf* srow = xb + g0 * L;                      // this thread's staged column
+            if constexpr (PC::SPLIT) srow = g0 < C / 2 ? sbuf + g0 * L : xb + (g0 - C / 2) * L;
             static_for<0, B0>([&](auto q_) {
                 constexpr int q = decltype(q_)::value;
                 static_for<0, R0>([&](auto t_) {
                     constexpr int t = decltype(t_)::value;
-                    v[q * R0 + bitrev<R0>(t)] = xb[g0 * L + j0 + q * T + t * STR0];
+                    v[q * R0 + bitrev<R0>(t)] = srow[j0 + q * T + t * STR0];
                 });
             });
             consumer_sync();
+            if constexpr (PC::SPLIT) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_free + 1)) : "memory");
             stage_math<T, E, R0, 1, INV, TW_NONE>(v, nullptr, p.table, 0, j0);
             stage_scatter<L, T, E, R0, 1, LOGPAD, DST_XCHG>(v, nullptr, xb + g0 * XBUF, j0, true);
             consumer_sync();
