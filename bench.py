@@ -470,7 +470,9 @@ def measure_dist(lg, rank, world, dev, barrier, steps=20, warmup=3):
         # every phase whose kernel crosses NVLink moves (P-1)/P * 8N/P bytes out of (and into) each GPU
         "nvlink_gbs": {f"{i}:{k}": round(exch / v / 1e6, 1) for i, (k, v) in enumerate(phases)
                        if world > 1 and v > 0 and ("push" in k or "pull" in k or k == "exchange")},
-        "nvlink_floor_ms": round(3 * exch / 900e9 * 1e3, 4) if world > 1 else None,
+        "nvlink_floor_ms": round(3 * exch / 900e9 * 1e3, 4) if world > 1 else None,             # three exchanges at the nominal 900 GB/s per direction
+        "nvlink_floor_measured_ms": round(3 * exch / 770e9 * 1e3, 4) if world > 1 else None,    # ... at the 770 GB/s a peer copy reaches (B200_PROFILING.md)
+        "frac_of_measured_floor": round(3 * exch / 770e9 * 1e3 / ms, 4) if world > 1 else None,
         "check": {"analytic_rel_rms": analytic_err, "parseval_rel": parseval, "tolerance": tol,
                   "ok": bool(analytic_err <= tol and parseval <= 1e-5)},
         "gpu_launches_per_step": len(phases),

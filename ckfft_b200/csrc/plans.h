@@ -86,15 +86,10 @@
 // (16384: the row does not leave room for a second buffer and the split prefetch needs the halves at different times,
 // but the twist needs the mirror pairs together; in-place prefetch measured .47 -> .55; with register twiddles on top .49.)
 // (shorter rows lose: in-place prefetch at M = 128 / 256 / 512 / 1024 measured .75 -> .63, .95 -> .69, .85 -> .70, .95 -> .81)
-#ifndef CKB_C2R_8192_G      /* development A/B switches (tools/exp_build.sh) */
-#define CKB_C2R_8192_G 1
-#define CKB_C2R_8192_MINB 2
-#define CKB_C2R_8192_TWR 1
-#endif
 #define CKB_INPLACE_PREFETCH_PLANS_C2R(X) \
     X(2048,  32, 32, 32,  2,  4, 2, 1) \
     X(4096,  32, 32, 32,  4,  2, 2, 1) \
-    X(8192,  32, 32, 32,  8,  CKB_C2R_8192_G, CKB_C2R_8192_MINB, CKB_C2R_8192_TWR) \
+    X(8192,  32, 32, 32,  8,  1, 2, 1)      /* round 2: G = 1 x 2 CTAs with the LUT .73, G = 2 x 1 CTA .77 / .78, table factors .73 */ \
     X(16384, 32, 32, 32, 16,  1, 1, 1)      /* round 2: register twiddles + constant twist factors .53 -> .72 */
 
 #define CKB_MAX_SINGLE_PASS 16384   /* largest complex length done in one launch */

@@ -13,7 +13,7 @@ timeout 300 python tools/gpu_check.py > gpurun_out/parity_${TAG}.log 2>&1; grep 
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --no-cpu-baseline > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 tail -2 gpurun_out/launches_${TAG}.csv | cut -c1-200
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:fft_kernel -s 3 -c 2 -o gpurun_out/prof_c2c1024_${TAG} python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1
-for spec in "c2c 64" "r2c 64"; do set -- $spec
+for spec in "c2c 16384" "c2c 4096" "r2c 4096" "c2c 65536" "c2c 1048576"; do set -- $spec
   timeout 200 ncu --set full --clock-control none --import-source on -k regex:"small_kernel|fft_kernel|pipe_kernel" -s 2 -c 1 -o gpurun_out/prof_$1_$2_${TAG} python tools/prof_one.py $1 $2 27 > gpurun_out/ncu_$1_$2_${TAG}.log 2>&1; tail -1 gpurun_out/ncu_$1_$2_${TAG}.log
 done
 ls -la gpurun_out | tail -20
