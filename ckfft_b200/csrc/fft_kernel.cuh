@@ -529,7 +529,7 @@ struct Cfg {
     // with the per-element indices and at 0.84-0.86 with the lean ones -- ptxas then schedules the stage-0 loads just in time
     // (96 instead of 128 registers) and the groups spend 39 % instead of 26 % of their time waiting for their row.
 #ifndef CKB_LEGACY_SIZES
-#define CKB_LEGACY_SIZES (MODE_ == MODE_C2C && M_ == 2048 && !PLANAR_)
+#define CKB_LEGACY_SIZES (MODE_ == MODE_C2C && M_ == 2048)
 #endif
     static constexpr bool LIN = !(CKB_LEGACY_SIZES);
     // complex slots per group (+ slot M for the real modes).  Plans with several groups per half-warp (T = 4, 8) need a

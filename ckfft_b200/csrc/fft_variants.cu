@@ -162,14 +162,17 @@ cudaError_t CKB_FN(int M, const KernelParams& p, cudaStream_t s)
 #if CKB_VARIANT >= 5
     // split-complex rows: in-place prefetch when both planes are 16-byte aligned row by row
     if (prefetch_mode() && (((uintptr_t) p.in | (uintptr_t) p.in_im) & 15) == 0 && (p.in_stride & 3) == 0) {
+        switch (M) {           // split prefetch (the two planes are the two halves) where the plan table has it, else in place
+#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
+    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_SPLIT, TWR_ != 0, kAudio, true>>(p, s);
+            CKB_SPLIT_PREFETCH_PLANS_PLANAR(X)
+#undef X
+            default: break;
+        }
         switch (M) {
 #define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
     case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_INPLACE, TWR_ != 0, kAudio, true>>(p, s);
             CKB_INPLACE_PREFETCH_PLANS_PLANAR(X)
-#undef X
-#define X(M_, E_, R0_, R1_, R2_, G_, MINB_, TWR_) \
-    case M_: return launch_cfg<Cfg<M_, E_, R0_, R1_, R2_, G_, kInv, kMode, MINB_, PF_SPLIT, TWR_ != 0, kAudio, true>>(p, s);
-            CKB_SPLIT_PREFETCH_PLANS(X)
 #undef X
             default: break;
         }

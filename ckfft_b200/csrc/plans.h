@@ -38,8 +38,18 @@
 // stall samples on the mbarrier wait).  Measured (tools/exp_build.sh, fraction of the copy peak, in-place -> split):
 //   C2C 4096 (G = 3, LUT)  .88-.95 -> .995     C2C 8192 (G = 2, TWR)  .88 -> .97      C2C 2048 (G = 6) .96 -> .88 (stays in place)
 //   R2C M = 2048 (G = 6, LUT) .84-.90 -> .945 (config 3: .93 -> .96)      R2C M = 4096 (G = 3, TWR) .88 -> .93
-#define CKB_SPLIT_PREFETCH_PLANS(X) \
+#ifndef CKB_PLANAR_SPLIT_ALL      /* development A/B switch */
+#define CKB_PLANAR_SPLIT_ALL 1
+#endif
+#if CKB_PLANAR_SPLIT_ALL          /* split-complex rows: the plane of real parts and the plane of imaginary parts are the two halves */
+#define CKB_SPLIT_PREFETCH_PLANS_PLANAR(X) \
+    X(4096,  32, 32, 32,  4,  3, 1, 0) \
+    X(8192,  32, 32, 32,  8,  2, 1, 1) \
     X(16384, 32, 32, 32, 16,  1, 1, 1)
+#else
+#define CKB_SPLIT_PREFETCH_PLANS_PLANAR(X) \
+    X(16384, 32, 32, 32, 16,  1, 1, 1)
+#endif
 #define CKB_SPLIT_PREFETCH_PLANS_C2C(X) \
     X(4096,  32, 32, 32,  4,  3, 1, 0) \
     X(8192,  32, 32, 32,  8,  2, 1, 1) \
