@@ -570,19 +570,28 @@ def measure_e2e(args, spec, ctx, rank, world, local_rank, dev, barrier, host_bar
     px[...] = nx[:sub]
     py[...] = 0
     dtp = timed(lambda: call(ctx, px, py), 2)
+    same = bool(np.array_equal(py.view(np.uint32), ny[:sub].view(np.uint32)))
     os.environ["CKFFT_B200_PIN"] = "1"
     try:
         dtu = timed(lambda: call(ctx, px, py), 2)
     finally:
         os.environ.pop("CKFFT_B200_PIN", None)
+    os.environ["CKFFT_B200_PAGEABLE_PIPE"] = "0"
+    try:
+        dtd = timed(lambda: call(ctx, px, py), 2)
+    finally:
+        os.environ.pop("CKFFT_B200_PAGEABLE_PIPE", None)
     pageable = {"value": round(spec["bytes"] * sub * world / dtp / 1e9, 2), "unit": "GB/s", "ms_per_step": round(dtp * 1e3, 3),
-                "sample": f"{sub} of {batch} transforms per GPU in numpy (malloc) arrays: the driver stages pageable copies, "
-                          "so H2D / D2H do not overlap",
+                "sample": f"{sub} of {batch} transforms per GPU in numpy (malloc) arrays",
+                "path": "library-side staging: two teams of host threads copy chunks between the caller's pageable arrays and pinned "
+                        "slots while the copy engines and the GPU work on the neighbouring chunks (api.cu, run_host_pageable)",
+                "driver_staged": {"value": round(spec["bytes"] * sub * world / dtd / 1e9, 2), "ms_per_step": round(dtd * 1e3, 3),
+                                  "note": "CKFFT_B200_PAGEABLE_PIPE=0: cudaMemcpyAsync straight on the pageable arrays (the driver "
+                                          "stages them synchronously, H2D / D2H do not overlap)"},
                 "with_registration": {"value": round(spec["bytes"] * sub * world / dtu / 1e9, 2), "ms_per_step": round(dtu * 1e3, 3),
                                       "note": "CKFFT_B200_PIN=1: the call page-locks the arrays for its duration (cudaHostRegister + "
                                               "unregister inside the timed region)"},
                 "h2d_bytes_per_step": int(px.nbytes), "d2h_bytes_per_step": int(py.nbytes)}
-    same = bool(np.array_equal(py.view(np.uint32), ny[:sub].view(np.uint32)))
     pageable["bit_identical_to_pinned_path"] = same
     del px, py
     # ---- one process, one call, all GPUs: the multi-device scheduler behind the C ABI (rank 0 drives, the others wait) ----

@@ -16,7 +16,11 @@
 #include <string.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "ckfft/ckfft.h"
 #include "ckfft/ckfft_b200.h"
@@ -587,6 +591,217 @@ int run_host(const _CkFftContext* c, Kind kind, int n, const void* in, void* out
     return 1;
 }
 
+// ---- pageable host arrays: library-side staging ------------------------------------------------------------------------
+// What a drop-in caller of the reference hands over is malloc'ed memory.  cudaMemcpyAsync on it goes through the driver's
+// own bounce buffer, synchronously (measured: H2D 11 GB/s, D2H 21 GB/s, nothing overlaps: 13-15 GB/s end to end, less than
+// the reference reaches on the 16 host cores of the same box), and page-locking the arrays per call costs what it saves
+// (ScopedPin above).  So large calls on pageable arrays are staged by the library itself: a team of host threads copies
+// chunk i + 1 from the caller's array into a pinned slot while the copy engines move chunk i and the GPU transforms it, and
+// a second team behind an output thread copies finished chunks from their pinned slots into the caller's output array.
+// Both DMA directions, the kernels and both host copies overlap; the pinned slots stay with the calling thread.
+class CopyTeam
+{
+public:
+    explicit CopyTeam(int n) : n_(n < 1 ? 1 : n)
+    {
+        try {
+            th_.reserve((size_t) n_);
+            for (int i = 1; i < n_; ++i) th_.emplace_back([this, i] { loop(i); });
+        } catch (...) { }                          // out of threads: the team is as large as it got (the caller always copies, too)
+        n_ = 1 + (int) th_.size();
+    }
+    ~CopyTeam()
+    {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (std::thread& t : th_) t.join();
+    }
+    // blocking: the caller copies the first piece itself
+    void copy(void* dst, const void* src, size_t bytes)
+    {
+        { std::lock_guard<std::mutex> l(m_); dst_ = (char*) dst; src_ = (const char*) src; bytes_ = bytes; pending_ = n_ - 1; ++gen_; }
+        cv_.notify_all();
+        piece(0);
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [&] { return pending_ == 0; });
+    }
+
+private:
+    void piece(int i) const
+    {
+        const size_t per = ((bytes_ + (size_t) n_ - 1) / (size_t) n_ + 4095) & ~size_t(4095);     // whole pages per thread
+        const size_t lo = (size_t) i * per < bytes_ ? (size_t) i * per : bytes_;
+        const size_t hi = lo + per < bytes_ ? lo + per : bytes_;
+        if (hi > lo) memcpy(dst_ + lo, src_ + lo, hi - lo);
+    }
+    void loop(int i)
+    {
+        unsigned long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            piece(i);
+            std::lock_guard<std::mutex> l(m_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    unsigned long gen_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+    char* dst_ = nullptr;
+    const char* src_ = nullptr;
+    size_t bytes_ = 0;
+};
+
+// pinned host staging slots of the calling thread (kept between calls: cudaHostAlloc costs milliseconds)
+struct PinnedSlots
+{
+    static constexpr int kSlots = Staging::kSlots;
+    void* h_in[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    void* h_out[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    size_t in_cap = 0, out_cap = 0;
+    static cudaError_t grow(void* (&buf)[kSlots], size_t& cap, size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        for (int i = 0; i < kSlots; ++i) { if (buf[i]) cudaFreeHost(buf[i]); buf[i] = nullptr; }
+        cap = 0;
+        for (int i = 0; i < kSlots; ++i) {
+            cudaError_t e = cudaHostAlloc(&buf[i], bytes, cudaHostAllocPortable);
+            if (e != cudaSuccess) { buf[i] = nullptr; return e; }
+        }
+        cap = bytes;
+        return cudaSuccess;
+    }
+    cudaError_t reserve(size_t in_bytes, size_t out_bytes)
+    {
+        cudaError_t e = grow(h_in, in_cap, in_bytes);
+        return e != cudaSuccess ? e : grow(h_out, out_cap, out_bytes);
+    }
+    ~PinnedSlots()
+    {
+        for (int i = 0; i < kSlots; ++i) { if (h_in[i]) cudaFreeHost(h_in[i]); if (h_out[i]) cudaFreeHost(h_out[i]); }
+        cudaGetLastError();
+    }
+};
+thread_local PinnedSlots tl_pinned;
+
+constexpr size_t kPageableStageBytes = size_t(64) << 20;     // smaller calls are not worth the helper threads
+constexpr size_t kPageableMaxRowBytes = size_t(64) << 20;    // longer transforms (n > 2^23) would pin gigabytes of staging slots
+
+bool is_pageable(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+int host_copy_threads()
+{
+    static const int n = [] {
+        const char* e = getenv("CKFFT_B200_HOST_THREADS");
+        long v = e ? atol(e) : 0;
+        // per team (there are two): measured on the 16-core B200 box, 2 GiB in + 2 GiB out: 2 threads 22.9 GB/s, 4 35.8, 8 44.8
+        // (12 threads 34, 16 threads 41: two teams of 8 are the 16 cores; driver-staged copies 12.9, the reference on all 16 cores
+        // 37.5); the call is synchronous, the cores are the caller's
+        if (v <= 0) { v = (long) std::thread::hardware_concurrency() / 2; if (v < 2) v = 2; if (v > 8) v = 8; }
+        return (int) (v > 64 ? 64 : v);
+    }();
+    return n;
+}
+
+// returns 1 done, 0 failed, -1 not applicable (no helper thread could be started: the caller takes the plain path)
+int run_host_pageable(const _CkFftContext* c, Kind kind, int n, const void* in, void* out, size_t batch)
+{
+    const size_t ib = in_elems(kind, n) * in_elem_bytes(kind);
+    const size_t ob = out_elems(kind, n) * out_elem_bytes(kind);
+    static const size_t target = [] {                              // input bytes per chunk (default 16 MiB)
+        const char* e = getenv("CKFFT_B200_PAGEABLE_CHUNK_MB");
+        const long mb = e ? atol(e) : 0;
+        return size_t(mb > 0 && mb <= 1024 ? mb : 16) << 20;
+    }();
+    size_t per_chunk = target / ib;
+    if (per_chunk < 1) per_chunk = 1;
+    if (per_chunk > batch) per_chunk = batch;
+    const size_t nchunks = (batch + per_chunk - 1) / per_chunk;
+    const int slots = nchunks < (size_t) Staging::kSlots ? (int) nchunks : Staging::kSlots;
+    Staging& st = tl_staging;
+    PinnedSlots& ps = tl_pinned;
+    cudaError_t e = st.reserve(c->device, per_chunk * ib + 16, per_chunk * ob + 16, slots);
+    if (e == cudaSuccess) e = ps.reserve(per_chunk * ib, per_chunk * ob);
+    if (e != cudaSuccess) { set_error("staging allocation", e); cudaGetLastError(); return 0; }
+
+    const int team = host_copy_threads();
+    CopyTeam team_in(team), team_out(team);
+    std::mutex m;
+    std::condition_variable cv;
+    size_t queued = 0, copied = 0;          // chunks enqueued on the device / copied out to the caller's array
+    bool failed = false;
+    cudaError_t err = cudaSuccess;
+    const char* where = "";
+    auto fail = [&](const char* w, cudaError_t ce) {
+        { std::lock_guard<std::mutex> l(m); if (!failed) { failed = true; err = ce; where = w; } }
+        cv.notify_all();
+    };
+    const int device = c->device;
+    std::thread out_thread;
+    try {
+        out_thread = std::thread([&] {
+        cudaSetDevice(device);
+        for (size_t i = 0; i < nchunks; ++i) {
+            {
+                std::unique_lock<std::mutex> l(m);
+                cv.wait(l, [&] { return queued > i || failed; });
+                if (queued <= i) return;
+            }
+            const int slot = (int) (i % (size_t) slots);
+            const cudaError_t ce = cudaEventSynchronize(st.ev_out[slot]);
+            if (ce != cudaSuccess) { fail("D2H copy", ce); return; }
+            const size_t off = i * per_chunk, cnt = batch - off < per_chunk ? batch - off : per_chunk;
+            team_out.copy((char*) out + off * ob, ps.h_out[slot], cnt * ob);
+            { std::lock_guard<std::mutex> l(m); copied = i + 1; }
+            cv.notify_all();
+        }
+        });
+    } catch (...) {
+        return -1;                               // no thread to be had: the caller takes the plain path
+    }
+    for (size_t i = 0; i < nchunks; ++i) {
+        const int slot = (int) (i % (size_t) slots);
+        if (i >= (size_t) slots) {               // the slot's previous chunk has left for the caller's array (so its H2D copy is long done)
+            std::unique_lock<std::mutex> l(m);
+            cv.wait(l, [&] { return copied + (size_t) slots > i || failed; });
+            if (failed) break;
+        }
+        const size_t off = i * per_chunk, cnt = batch - off < per_chunk ? batch - off : per_chunk;
+        team_in.copy(ps.h_in[slot], (const char*) in + off * ib, cnt * ib);
+        if ((e = cudaMemcpyAsync(st.d_in[slot], ps.h_in[slot], cnt * ib, cudaMemcpyHostToDevice, st.s_in)) != cudaSuccess ||
+            (e = cudaEventRecord(st.ev_in[slot], st.s_in)) != cudaSuccess) { fail("H2D copy", e); break; }
+        if ((e = cudaStreamWaitEvent(st.s_k, st.ev_in[slot], 0)) == cudaSuccess)
+            e = enqueue(c, kind, n, st.d_in[slot], st.d_out[slot], (long long) cnt,
+                        (long long) in_elems(kind, n), (long long) out_elems(kind, n), st.s_k);
+        if (e == cudaSuccess) e = cudaEventRecord(st.ev_k[slot], st.s_k);
+        if (e != cudaSuccess) { fail("kernel launch", e); break; }
+        if ((e = cudaStreamWaitEvent(st.s_out, st.ev_k[slot], 0)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(ps.h_out[slot], st.d_out[slot], cnt * ob, cudaMemcpyDeviceToHost, st.s_out)) != cudaSuccess ||
+            (e = cudaEventRecord(st.ev_out[slot], st.s_out)) != cudaSuccess) { fail("D2H copy", e); break; }
+        { std::lock_guard<std::mutex> l(m); queued = i + 1; }
+        cv.notify_all();
+    }
+    out_thread.join();
+    e = st.drain();
+    if (failed) { set_error(where, err); return 0; }
+    if (e != cudaSuccess) { set_error("transform failed", e); return 0; }
+    return 1;
+}
+
 bool supported_size(const _CkFftContext* c, Kind kind, int n)
 {
     (void) c; (void) kind;
@@ -608,7 +823,14 @@ int run_sync(CkFftContext* c, Kind kind, int n, const void* in, void* out, size_
     }
     if (si == SIDE_HOST) {
         const int small = run_host_small(c, kind, n, in, out, batch);
-        return small >= 0 ? small : run_host(c, kind, n, in, out, batch);
+        if (small >= 0) return small;
+        const size_t bytes = (in_elems(kind, n) * in_elem_bytes(kind) + out_elems(kind, n) * out_elem_bytes(kind)) * batch;
+        if (bytes >= kPageableStageBytes && getenv_flag("CKFFT_B200_PAGEABLE_PIPE", 1) && !getenv_flag("CKFFT_B200_PIN", 0) &&
+            in_elems(kind, n) * in_elem_bytes(kind) <= kPageableMaxRowBytes && is_pageable(in) && is_pageable(out)) {
+            const int staged = run_host_pageable(c, kind, n, in, out, batch);
+            if (staged >= 0) return staged;
+        }
+        return run_host(c, kind, n, in, out, batch);
     }
     if (((uintptr_t) in | (uintptr_t) out) & 7) { set_error("device pointers must be 8-byte aligned"); return 0; }
     cudaError_t e = enqueue(c, kind, n, in, out, (long long) batch, (long long) in_elems(kind, n),

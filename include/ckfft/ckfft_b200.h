@@ -88,8 +88,8 @@ typedef struct
     int radix[2][3];          /* radices of each pass, 0-terminated */
     int threadsPerTransform;  /* threads cooperating on one transform (first pass) */
     int elemsPerThread;       /* complex values held in registers per thread */
-    int transformsPerCta;
-    int sharedBytes;          /* dynamic shared memory per CTA */
+    int transformsPerCta;     /* of the plain-load plan (any alignment / stride); the bulk-prefetch kernels that take 16-byte aligned */
+    int sharedBytes;          /* rows run the same radices with their own grouping and staging buffers (csrc/plans.h) */
 } CkFftB200Plan;
 
 /* returns 1 and fills *plan, or 0 if n is not a supported power of two */
