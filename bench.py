@@ -654,6 +654,10 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, spec, rank)
         return
+    if world > 1 and "CKFFT_B200_HOST_THREADS" not in os.environ:
+        # the library's pageable-array staging uses two teams of host threads per calling process (default: half the hardware
+        # threads each, at most 8); N ranks share one host, so every rank takes its share of the cores
+        os.environ["CKFFT_B200_HOST_THREADS"] = str(max(1, min(8, (os.cpu_count() or 16) // (2 * world))))
 
     import torch
     import torch.distributed as dist
