@@ -718,7 +718,13 @@ int host_copy_threads()
 }
 
 // returns 1 done, 0 failed, -1 not applicable (no helper thread could be started: the caller takes the plain path)
-int run_host_pageable(const _CkFftContext* c, Kind kind, int n, const void* in, void* out, size_t batch)
+// Threads of ONE call that share the host with sibling calls of the same batch (the multi-device scheduler's workers, multi.cu)
+// divide the copy teams among them.
+thread_local int tl_host_sharers = 1;
+
+// `cursor` (multi-device scheduler): this thread's device works on a batch it shares with other devices and draws chunk numbers
+// from the shared counter, like run_host.
+int run_host_pageable(const _CkFftContext* c, Kind kind, int n, const void* in, void* out, size_t batch, std::atomic<size_t>* cursor = nullptr)
 {
     const size_t ib = in_elems(kind, n) * in_elem_bytes(kind);
     const size_t ob = out_elems(kind, n) * out_elem_bytes(kind);
@@ -730,6 +736,10 @@ int run_host_pageable(const _CkFftContext* c, Kind kind, int n, const void* in, 
     size_t per_chunk = target / ib;
     if (per_chunk < 1) per_chunk = 1;
     if (per_chunk > batch) per_chunk = batch;
+    if (cursor) {                                   // shared batch: every thread derives the same chunk size, all devices get work
+        const size_t share = (batch + 63) / 64;
+        if (per_chunk > share) per_chunk = share ? share : 1;
+    }
     const size_t nchunks = (batch + per_chunk - 1) / per_chunk;
     const int slots = nchunks < (size_t) Staging::kSlots ? (int) nchunks : Staging::kSlots;
     Staging& st = tl_staging;
@@ -738,11 +748,14 @@ int run_host_pageable(const _CkFftContext* c, Kind kind, int n, const void* in, 
     if (e == cudaSuccess) e = ps.reserve(per_chunk * ib, per_chunk * ob);
     if (e != cudaSuccess) { set_error("staging allocation", e); cudaGetLastError(); return 0; }
 
-    const int team = host_copy_threads();
+    const int team = host_copy_threads() / tl_host_sharers > 1 ? host_copy_threads() / tl_host_sharers : 1;
     CopyTeam team_in(team), team_out(team);
     std::mutex m;
     std::condition_variable cv;
-    size_t queued = 0, copied = 0;          // chunks enqueued on the device / copied out to the caller's array
+    size_t queued = 0, copied = 0;          // this thread's chunks enqueued on the device / copied out to the caller's array
+    std::vector<size_t> drawn;              // their positions in the batch (local chunk k = chunk drawn[k] of the batch)
+    drawn.reserve(nchunks);
+    bool closed = false;                    // no more chunks will be queued
     bool failed = false;
     cudaError_t err = cudaSuccess;
     const char* where = "";
@@ -755,16 +768,18 @@ int run_host_pageable(const _CkFftContext* c, Kind kind, int n, const void* in, 
     try {
         out_thread = std::thread([&] {
         cudaSetDevice(device);
-        for (size_t i = 0; i < nchunks; ++i) {
+        for (size_t i = 0;; ++i) {
+            size_t ci;
             {
                 std::unique_lock<std::mutex> l(m);
-                cv.wait(l, [&] { return queued > i || failed; });
+                cv.wait(l, [&] { return queued > i || closed || failed; });
                 if (queued <= i) return;
+                ci = drawn[i];
             }
             const int slot = (int) (i % (size_t) slots);
             const cudaError_t ce = cudaEventSynchronize(st.ev_out[slot]);
             if (ce != cudaSuccess) { fail("D2H copy", ce); return; }
-            const size_t off = i * per_chunk, cnt = batch - off < per_chunk ? batch - off : per_chunk;
+            const size_t off = ci * per_chunk, cnt = batch - off < per_chunk ? batch - off : per_chunk;
             team_out.copy((char*) out + off * ob, ps.h_out[slot], cnt * ob);
             { std::lock_guard<std::mutex> l(m); copied = i + 1; }
             cv.notify_all();
@@ -773,14 +788,16 @@ int run_host_pageable(const _CkFftContext* c, Kind kind, int n, const void* in, 
     } catch (...) {
         return -1;                               // no thread to be had: the caller takes the plain path
     }
-    for (size_t i = 0; i < nchunks; ++i) {
+    for (size_t i = 0;; ++i) {
+        const size_t ci = cursor ? cursor->fetch_add(1, std::memory_order_relaxed) : i;      // next (unclaimed) chunk of the batch
+        if (ci >= nchunks) break;
         const int slot = (int) (i % (size_t) slots);
         if (i >= (size_t) slots) {               // the slot's previous chunk has left for the caller's array (so its H2D copy is long done)
             std::unique_lock<std::mutex> l(m);
             cv.wait(l, [&] { return copied + (size_t) slots > i || failed; });
             if (failed) break;
         }
-        const size_t off = i * per_chunk, cnt = batch - off < per_chunk ? batch - off : per_chunk;
+        const size_t off = ci * per_chunk, cnt = batch - off < per_chunk ? batch - off : per_chunk;
         team_in.copy(ps.h_in[slot], (const char*) in + off * ib, cnt * ib);
         if ((e = cudaMemcpyAsync(st.d_in[slot], ps.h_in[slot], cnt * ib, cudaMemcpyHostToDevice, st.s_in)) != cudaSuccess ||
             (e = cudaEventRecord(st.ev_in[slot], st.s_in)) != cudaSuccess) { fail("H2D copy", e); break; }
@@ -792,9 +809,11 @@ int run_host_pageable(const _CkFftContext* c, Kind kind, int n, const void* in, 
         if ((e = cudaStreamWaitEvent(st.s_out, st.ev_k[slot], 0)) != cudaSuccess ||
             (e = cudaMemcpyAsync(ps.h_out[slot], st.d_out[slot], cnt * ob, cudaMemcpyDeviceToHost, st.s_out)) != cudaSuccess ||
             (e = cudaEventRecord(st.ev_out[slot], st.s_out)) != cudaSuccess) { fail("D2H copy", e); break; }
-        { std::lock_guard<std::mutex> l(m); queued = i + 1; }
+        { std::lock_guard<std::mutex> l(m); drawn.push_back(ci); queued = i + 1; }
         cv.notify_all();
     }
+    { std::lock_guard<std::mutex> l(m); closed = true; }
+    cv.notify_all();
     out_thread.join();
     e = st.drain();
     if (failed) { set_error(where, err); return 0; }
@@ -806,6 +825,14 @@ bool supported_size(const _CkFftContext* c, Kind kind, int n)
 {
     (void) c; (void) kind;
     return n <= (1 << 30);    // single pass up to 16384 complex / 32768 real points, multi-pass above
+}
+
+// large calls on two pageable arrays go through the library's own staging (run_host_pageable)
+bool wants_pageable_staging(Kind kind, int n, const void* in, const void* out, size_t batch)
+{
+    const size_t ib = in_elems(kind, n) * in_elem_bytes(kind), ob = out_elems(kind, n) * out_elem_bytes(kind);
+    return (ib + ob) * batch >= kPageableStageBytes && ib <= kPageableMaxRowBytes && getenv_flag("CKFFT_B200_PAGEABLE_PIPE", 1) &&
+           !getenv_flag("CKFFT_B200_PIN", 0) && is_pageable(in) && is_pageable(out);
 }
 
 // shared body of the synchronous entry points
@@ -824,9 +851,7 @@ int run_sync(CkFftContext* c, Kind kind, int n, const void* in, void* out, size_
     if (si == SIDE_HOST) {
         const int small = run_host_small(c, kind, n, in, out, batch);
         if (small >= 0) return small;
-        const size_t bytes = (in_elems(kind, n) * in_elem_bytes(kind) + out_elems(kind, n) * out_elem_bytes(kind)) * batch;
-        if (bytes >= kPageableStageBytes && getenv_flag("CKFFT_B200_PAGEABLE_PIPE", 1) && !getenv_flag("CKFFT_B200_PIN", 0) &&
-            in_elems(kind, n) * in_elem_bytes(kind) <= kPageableMaxRowBytes && is_pageable(in) && is_pageable(out)) {
+        if (wants_pageable_staging(kind, n, in, out, batch)) {
             const int staged = run_host_pageable(c, kind, n, in, out, batch);
             if (staged >= 0) return staged;
         }
@@ -890,8 +915,16 @@ int run_host_shared(CkFftContext* c, int kind, int n, const void* in, void* out,
     if (!c || c->magic != kMagic) { set_error("invalid context"); return 0; }
     DeviceGuard guard(c->device);
     if (!guard.ok) { set_error("cannot select the context's device"); return 0; }
+    if (wants_pageable_staging((Kind) kind, n, in, out, batch)) {
+        const int staged = run_host_pageable(c, (Kind) kind, n, in, out, batch, cursor);
+        // (-1 = no helper thread to be had BEFORE any chunk was drawn: the plain path takes over)
+        if (staged >= 0) return staged;
+    }
     return run_host(c, (Kind) kind, n, in, out, batch, cursor);
 }
+
+// multi.cu: how many worker threads of one BatchMulti call share the host (divides the pageable-staging copy teams)
+void set_host_sharers(int n) { tl_host_sharers = n < 1 ? 1 : n; }
 
 // Stream-ordered scratch from the library's OWN memory pool (one per device).  The default pool of cudaMallocAsync
 // gives unused memory back to the driver at every synchronisation (release threshold 0), so a caller who synchronises

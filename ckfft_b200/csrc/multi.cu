@@ -11,7 +11,8 @@
 //   CkFft*BatchMulti        shard -> post to the workers -> join; returns 1 only if every shard returned 1
 //   CkFftB200ShardRange     the shard arithmetic itself (pure host code; bench.py and the tests use the same function)
 //
-// Pageable host memory: cudaMemcpyAsync on it is staged by the driver and synchronous.  With CKFFT_B200_PIN=1 a call that
+// Pageable host memory: every worker stages its chunks through pinned slots with its share of the host's copy threads
+// (api.cu, run_host_pageable; set_host_sharers below).  With CKFFT_B200_PIN=1 instead a call that
 // moves at least kPinThreshold bytes page-locks the caller's arrays for its duration (cudaHostRegister, portable across
 // the devices); off by default because registration costs as much as it saves (api.cu, ScopedPin).  Arrays that are
 // already pinned are left alone.
@@ -36,6 +37,7 @@
 namespace ckb {                                             // api.cu
 void set_last_error(const char* text);
 int run_host_shared(CkFftContext* c, int kind, int n, const void* in, void* out, size_t batch, std::atomic<size_t>* cursor);
+void set_host_sharers(int n);
 }
 
 namespace {
@@ -63,6 +65,7 @@ struct Job {
     void* out = nullptr;
     size_t batch = 0;
     std::atomic<size_t>* cursor = nullptr;     // dynamic schedule: the whole batch + a shared chunk counter; static: this worker's shard
+    int parts = 1;                             // workers of this call
 };
 
 struct Worker {
@@ -107,6 +110,7 @@ void worker_main(Worker* w, int nMax, CkFftDirection dir)
             w->has_job = false;
         }
         int r = 1;
+        ckb::set_host_sharers(j.parts);                    // pageable arrays: the workers of one call divide the host's copy threads
         if (j.batch > 0 && j.cursor) {
             r = ckb::run_host_shared(w->ctx, j.kind - JOB_C2C_FWD, j.n, j.in, j.out, j.batch, j.cursor);
         } else if (j.batch > 0) {
@@ -313,6 +317,7 @@ static int run_multi(CkFftB200Multi* m, int kind, int n, const void* in, void* o
             w->job.out = dynamic ? out : (void*) ((char*) out + first * ob);
             w->job.batch = dynamic ? batch : count;
             w->job.cursor = dynamic ? &cursor : nullptr;
+            w->job.parts = parts;
             w->done = false;
             w->has_job = true;
         }

@@ -58,3 +58,20 @@ def test_pageable_long_transforms():
         want = ctx.complex_forward(torch.from_numpy(x).cuda()).cpu().numpy()
         got = ctx.complex_forward(x)
         assert np.array_equal(bits(got), bits(want))
+
+
+@pytest.mark.parametrize("static", ["0", "1"])
+def test_pageable_arrays_through_the_multi_device_scheduler(static, monkeypatch):
+    """>= 256 MiB on pageable arrays: the workers of one BatchMulti call draw chunks of the shared batch (dynamic schedule) or take
+    contiguous shards (static) and stage them through their own pinned slots, dividing the host's copy threads among them"""
+    monkeypatch.setenv("CKFFT_B200_MULTI_STATIC", static)
+    n, batch = 4096, 9001                                       # 147 MB in + 148 MB out
+    rng = np.random.default_rng(8)
+    x = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    devices = list(range(torch.cuda.device_count())) if torch.cuda.device_count() >= 2 else [0, 0, 0]
+    with ck.Context(n, ck.BOTH) as ctx, ck.MultiContext(n, ck.BOTH, devices) as mc:
+        want = ctx.real_forward(torch.from_numpy(x).cuda()).cpu().numpy()
+        got = mc.real_forward(x)
+        assert np.array_equal(bits(got), bits(want))
+        back = mc.real_inverse(got, n)
+        assert np.array_equal(bits(back), bits(ctx.real_inverse(torch.from_numpy(want).cuda(), n).cpu().numpy()))
