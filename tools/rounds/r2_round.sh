@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2 GPU visit: suite, smoke, both bench arms, two-pass sweep A/B, one ncu capture.  bash tools/r2_round.sh <tag>
+# Round-2 GPU visit: suite, smoke, both bench arms, two-pass sweep A/B, one ncu capture.  bash tools/rounds/r2_round.sh <tag>
 mkdir -p gpurun_out
 TAG=${1:-r2a}
 SECONDS=0

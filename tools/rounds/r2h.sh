@@ -1,4 +1,4 @@
-# round 2, closing multi-GPU visit: bash tools/r2h.sh <N> [tests]   (gpurun --gpus N)
+# round 2, closing multi-GPU visit: bash tools/rounds/r2h.sh <N> [tests]   (gpurun --gpus N)
 N=$1; mkdir -p gpurun_out; SECONDS=0; TAG=r2h
 if [ "$2" = tests ]; then
   timeout 1500 python -m pytest tests -m gpu -q --maxfail=8 > gpurun_out/pytest_gpu_${N}gpu_${TAG}.log 2>&1; echo "pytest rc=$? after ${SECONDS}s"; tail -3 gpurun_out/pytest_gpu_${N}gpu_${TAG}.log
