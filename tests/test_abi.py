@@ -37,6 +37,17 @@ def test_library_exports_every_declared_symbol():
     assert not extra, f"exported but not declared: {extra}"
 
 
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md is the binding guide of the drop-in boundary: every function the headers declare appears in it
+    (brace groups such as CkFft{ComplexForward,RealForward}Batch are expanded)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    named = set(re.findall(r"\bCkFft\w+", text))
+    for m in re.finditer(r"(CkFft\w*)\{([^}]*)\}(\w*)", text):
+        named |= {m.group(1) + alt.strip() + m.group(3) for alt in m.group(2).split(",")}
+    declared = declared_functions("ckfft.h") | declared_functions("ckfft_b200.h")
+    assert not declared - named, f"not documented in INTEGRATION.md: {sorted(declared - named)}"
+
+
 def test_classic_header_is_the_reference_surface():
     """the six functions of inc/ckfft/ckfft.h:59-158, nothing more"""
     assert declared_functions("ckfft.h") == {"CkFftInit", "CkFftRealForward", "CkFftRealInverse",
