@@ -35,6 +35,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-fvisibi
 UNITS = [
     ("api.o", "api.cu", []),
     ("multi.o", "multi.cu", []),
+    ("host_copy.o", "host_copy.cpp", []),
     ("tiny.o", "tiny.cu", []),
     ("small.o", "small.cu", []),
     ("four_step.o", "four_step.cu", []),
