@@ -583,8 +583,8 @@ def measure_e2e(args, spec, ctx, rank, world, local_rank, dev, barrier, host_bar
         os.environ.pop("CKFFT_B200_PAGEABLE_PIPE", None)
     pageable = {"value": round(spec["bytes"] * sub * world / dtp / 1e9, 2), "unit": "GB/s", "ms_per_step": round(dtp * 1e3, 3),
                 "sample": f"{sub} of {batch} transforms per GPU in numpy (malloc) arrays",
-                "path": "library-side staging: two teams of host threads copy chunks between the caller's pageable arrays and pinned "
-                        "slots while the copy engines and the GPU work on the neighbouring chunks (api.cu, run_host_pageable)",
+                "path": "library-side staging: two teams of host threads copy chunks (non-temporal stores, host_copy.cpp) between the caller's "
+                        "pageable arrays and pinned slots while the copy engines and the GPU work on the neighbouring chunks (api.cu, run_host_pageable)",
                 "driver_staged": {"value": round(spec["bytes"] * sub * world / dtd / 1e9, 2), "ms_per_step": round(dtd * 1e3, 3),
                                   "note": "CKFFT_B200_PAGEABLE_PIPE=0: cudaMemcpyAsync straight on the pageable arrays (the driver "
                                           "stages them synchronously, H2D / D2H do not overlap)"},
